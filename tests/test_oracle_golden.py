@@ -1,0 +1,139 @@
+"""CPU: the oracle restatement against golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  This is what pins oracle/mvsnerf_oracle.py."""
+import torch
+
+from oracle import mvsnerf_oracle as orc
+
+TOL_VOL = 2e-4      # |volume| <= ~12; fp32 summation-order noise of train-mode BN is ~6e-6
+TOL_RGB = 2e-6
+
+
+def pose_of(g):
+    return {"w2cs": g["w2cs"], "c2ws": g["c2ws"], "intrinsics": g["intrinsics"]}
+
+
+def dims(g):
+    H, W, pad = (int(v) for v in g["HW_pad"])
+    return H, W, pad
+
+
+def test_feature_net(golden_tiny, weights):
+    g = golden_tiny
+    f = orc.feature_net(g["imgs_norm"][0], weights)
+    assert f.shape == g["feats"].shape
+    assert (f - g["feats"]).abs().max() < 1e-4
+
+
+def test_depth_planes(golden_tiny, golden_tiny_lindisp):
+    for g, lin in ((golden_tiny, False), (golden_tiny_lindisp, True)):
+        d = orc.depth_planes(float(g["near_far"][0]), float(g["near_far"][1]), lindisp=lin)
+        assert torch.allclose(d, g["depth_values"], rtol=0, atol=1e-6)
+
+
+def test_cost_volume(golden_tiny, weights):
+    g = golden_tiny
+    H, W, pad = dims(g)
+    cv, masks = orc.cost_volume(g["imgs_norm"][0], g["feats"], g["proj_mats"][0], g["depth_values"], pad)
+    idx = g["vox_idx"]
+    assert torch.equal(masks.reshape(3, -1)[:, idx], g["in_masks_sub"])
+    assert torch.allclose(cv.reshape(41, -1)[:, idx], g["cost_volume_sub"], rtol=1e-5, atol=1e-5)
+    assert torch.allclose(cv.double().sum((1, 2, 3)), g["cost_volume_chsum"], rtol=1e-5, atol=1e-2)
+    # F5: the never-written border of channels 0:3 is zero
+    assert cv[:3, :, :pad].abs().max() == 0 and cv[:3, :, :, :pad].abs().max() == 0
+
+
+def test_cost_reg_net_and_volume(golden_tiny, weights):
+    g = golden_tiny
+    H, W, pad = dims(g)
+    vol, st = orc.encode_volume(g["imgs_norm"], g["proj_mats"], g["near_far"].tolist(), pad, weights,
+                                return_stages=True)
+    assert vol.shape == g["volume"].shape
+    assert (vol - g["volume"]).abs().max() < TOL_VOL
+
+
+def test_volume_lindisp(golden_tiny_lindisp, weights):
+    g = golden_tiny_lindisp
+    H, W, pad = dims(g)
+    vol = orc.encode_volume(g["imgs_norm"], g["proj_mats"], g["near_far"].tolist(), pad, weights, lindisp=True)
+    assert (vol - g["volume"]).abs().max() < TOL_VOL
+
+
+def test_ray_march_and_ndc(golden_tiny):
+    g = golden_tiny
+    H, W, pad = dims(g)
+    pts, z = orc.march_rays(g["rays"], 32)
+    assert torch.equal(z, g["z"])
+    ndc = orc.ndc_coords(g["w2cs"][0], g["intrinsics"][0], pts, H, W, float(g["near_far"][0]),
+                         float(g["near_far"][1]), float(pad))
+    assert (ndc - g["ndc"]).abs().max() < 1e-6
+    pts, z = orc.march_rays(g["rays"][:256], 16, lindisp=True)
+    ndc = orc.ndc_coords(g["w2cs"][0], g["intrinsics"][0], pts, H, W, float(g["near_far"][0]),
+                         float(g["near_far"][1]), float(pad), lindisp=True)
+    assert (ndc - g["ndc_lindisp256"]).abs().max() < 1e-5
+
+
+def test_render_tiny(golden_tiny, weights):
+    g = golden_tiny
+    H, W, pad = dims(g)
+    rays = g["rays"]
+    pts, z = orc.march_rays(rays, 32)
+    rgb, feat, wts, depth, alpha = orc.render_samples(pts, g["ndc"], z, rays[:, 3:6], g["volume"],
+                                                      g["imgs_raw"], pose_of(g), weights)
+    assert (feat[:128] - g["feat_first128"]).abs().max() < 1e-5
+    assert (rgb - g["rgb"]).abs().max() < TOL_RGB
+    assert (depth - g["depth"]).abs().max() < 1e-5
+    assert (wts - g["weights"]).abs().max() < TOL_RGB
+    assert (alpha - g["alpha"]).abs().max() < TOL_RGB
+
+
+def test_render_variants(golden_tiny, weights):
+    g = golden_tiny
+    H, W, pad = dims(g)
+    nf = g["near_far"].tolist()
+    rgb, _ = orc.render_rays(g["rays"][:256], g["volume"], g["imgs_raw"], pose_of(g), weights, H, W, nf,
+                             float(pad), n_samples=32, white_bkgd=True)
+    assert (rgb - g["rgb_white256"]).abs().max() < TOL_RGB
+    rgb, depth = orc.render_rays(g["rays"][:256], g["volume"], g["imgs_raw"], pose_of(g), weights, H, W, nf,
+                                 float(pad), n_samples=16, lindisp=True)
+    assert (rgb - g["rgb_lindisp256"]).abs().max() < TOL_RGB
+    assert (depth - g["depth_lindisp256"]).abs().max() < 1e-5
+
+
+def test_config1_end_to_end(golden_c1, weights):
+    """BASELINE config 1: 64x64 crop, 3 views, pad 24, N_samples 32, CPU forward from the v0 weights."""
+    g = golden_c1
+    H, W, pad = dims(g)
+    nf = g["near_far"].tolist()
+    vol, st = orc.encode_volume(g["imgs_norm"], g["proj_mats"], nf, pad, weights, return_stages=True)
+    idx = g["vox_idx"]
+    assert torch.equal(st["in_masks"].reshape(3, -1)[:, idx], g["in_masks_sub"])
+    # variance channels reach ~2e2 (E[x^2]-E[x]^2 cancellation): tolerance is relative to that scale
+    assert torch.allclose(st["cost_volume"].reshape(41, -1)[:, idx], g["cost_volume_sub"], rtol=1e-5, atol=1e-4)
+    assert (vol[0].reshape(8, -1)[:, idx] - g["volume_sub"]).abs().max() < TOL_VOL
+    assert torch.allclose(vol[0].double().sum((1, 2, 3)), g["volume_chsum"], rtol=1e-4, atol=0.5)
+    rgb, depth = orc.render_rays(g["rays"], vol, g["imgs_raw"], pose_of(g), weights, H, W, nf, float(pad),
+                                 n_samples=32)
+    assert (rgb - g["rgb"]).abs().max() < 2e-5      # volume noise (<=2e-4) propagates ~0.1x
+    assert (depth - g["depth"]).abs().max() < 2e-4
+    rgb, depth = orc.render_rays(g["rays"][1024:1280], vol, g["imgs_raw"], pose_of(g), weights, H, W, nf,
+                                 float(pad), n_samples=128)
+    assert (rgb - g["rgb128"]).abs().max() < 2e-5
+
+
+def test_manual_samplers_match_grid_sample():
+    """Pins SURVEY.md App. A1 tap arithmetic (what the CUDA kernels implement) to F.grid_sample."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    src = torch.rand(5, 9, 11, generator=g)
+    grid = torch.rand(1, 40, 30, 2, generator=g) * 2.6 - 1.3
+    grid[0, 0, 0] = torch.tensor([-1.0, -1.0]); grid[0, 0, 1] = torch.tensor([1.0, 1.0])
+    for border in (False, True):
+        ref = F.grid_sample(src[None], grid, mode="bilinear", align_corners=True,
+                            padding_mode="border" if border else "zeros")[0]
+        got = orc.bilinear_manual(src, grid[0, ..., 0], grid[0, ..., 1], border)
+        assert (ref - got).abs().max() < 1e-5
+    vol = torch.rand(1, 4, 6, 7, 8, generator=g)
+    n = torch.rand(50, 9, 3, generator=g) * 1.4 - 0.2
+    ref = orc.lookup_volume(vol, n)
+    got = orc.trilinear_manual(vol[0], n)
+    assert (ref - got).abs().max() < 1e-5

@@ -1,0 +1,45 @@
+"""CPU, build container only: the oracle restatement next to the LIVE unmodified reference
+(imported through oracle/ref_shim.py) on a fresh seeded scene.  Skipped where /root/reference
+is absent (the GPU box) -- the committed golden vectors cover that case."""
+import pytest
+import torch
+
+from oracle import mvsnerf_oracle as orc
+from oracle import ref_shim
+from mvsnerf_b200 import synthetic
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def live():
+    return ref_shim.build_reference(N_samples=24)
+
+
+def test_weights_fixture_matches_checkpoint(live, weights):
+    sd = live.render_kwargs["network_fn"].state_dict()
+    for k, v in sd.items():
+        assert torch.equal(v.cpu(), weights["mlp/" + k]), k
+    n = sum(1 for k in weights if k.startswith("mvs/"))
+    assert n == len(live.mvsnet.state_dict()) == 110
+
+
+def test_live_reference_vs_oracle(live, weights):
+    sc = synthetic.make_scene(64, 96, pad=4, seed=11)     # h=16,w=24 -> 24x32 padded: legal
+    ref = live.ref
+    with torch.no_grad():
+        vol_ref, _, _ = live.mvsnet(sc.imgs_norm, sc.proj_mats, sc.near_far, pad=sc.pad)
+    vol = orc.encode_volume(sc.imgs_norm, sc.proj_mats, sc.near_far, sc.pad, weights)
+    assert (vol - vol_ref).abs().max() < 2e-4
+    rays = synthetic.scene_rays(sc)[::5]
+    with torch.no_grad():
+        xyz, ro, rd, z = ref.ray_utils.ray_marcher(rays, N_samples=24)
+        ndc = ref.utils.get_ndc_coordinate(sc.pose_source["w2cs"][0], sc.pose_source["intrinsics"][0].clone(),
+                                           xyz, torch.tensor([sc.W - 1, sc.H - 1]), near=sc.near_far[0],
+                                           far=sc.near_far[1], pad=sc.pad * 1.0)
+        rgb_ref, feat_ref, w_ref, depth_ref, alpha_ref, _ = ref.renderer.rendering(
+            live.args, sc.pose_source, xyz, ndc, z, ro, rd, vol_ref, sc.imgs_raw, **live.render_kwargs)
+    rgb, depth = orc.render_rays(rays, vol_ref, sc.imgs_raw, sc.pose_source, weights, sc.H, sc.W,
+                                 sc.near_far, float(sc.pad), n_samples=24)
+    assert (rgb - rgb_ref).abs().max() < 2e-6
+    assert (depth - depth_ref).abs().max() < 1e-5
