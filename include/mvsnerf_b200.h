@@ -1,0 +1,160 @@
+/*
+ * mvsnerf_b200 -- C ABI of the B200-native MVSNeRF render hot path.
+ *
+ * The reference (apchenstu/mvsnerf) has no FFI layer: the hot path sits behind
+ * plain Python callables.  Each entry point below replaces the
+ * arithmetic of one of those callables; the Python mirror of the reference's
+ * call signatures lives in mvsnerf_b200/backend.py and binds this header with
+ * ctypes (INTEGRATION.md shows the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - all tensors are dense fp32 unless stated, layouts are written as C arrays;
+ *   - the caller owns every buffer (including workspaces); the library allocates
+ *     nothing and keeps no state between calls;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     the call returns without synchronising;
+ *   - return value: 0 on success, a negative MVSN_E* code otherwise; the text of
+ *     the last error on the calling thread is available from mvsn_last_error();
+ *     nothing ever throws across this boundary.
+ */
+#ifndef MVSNERF_B200_H
+#define MVSNERF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVSN_OK          0
+#define MVSN_EBADSHAPE  -1   /* illegal size (e.g. padded volume dims not divisible by 8)   */
+#define MVSN_EALIGN     -2   /* pointer not 16-byte aligned where the kernel needs it       */
+#define MVSN_ECUDA      -3   /* a CUDA call failed; see mvsn_last_error()                   */
+#define MVSN_ENULL      -4   /* required pointer is NULL                                    */
+#define MVSN_EWORKSPACE -5   /* workspace too small                                         */
+#define MVSN_EUNSUPPORTED -6 /* feature/mode not available                                  */
+
+/* arithmetic modes of the per-sample MLP (the GEMMs inside the render kernel) */
+#define MVSN_MLP_FP32        0  /* fp32 FFMA, parity <= 1e-4 RGB Linf (north-star fp32 gate)        */
+#define MVSN_MLP_TC_HALF     1  /* tcgen05 kind::f16 operands, fp32 accumulate, gate 5e-3           */
+#define MVSN_MLP_TC_SPLIT    2  /* tcgen05, 2-term fp16 operand split (3 MMAs), fp32-grade, 1e-4    */
+
+#define MVSN_N_MLP_TENSORS   22 /* network_fn_state_dict, reference models.py:145-222 / SURVEY App. B */
+#define MVSN_N_COSTREG_TENSORS 30 /* 10 x (conv weight, bn gamma, bn beta), models.py:725-769          */
+#define MVSN_VOL_CH          8
+#define MVSN_COST_CH         41
+#define MVSN_FEAT_CH         32
+
+const char* mvsn_last_error(void);
+int mvsn_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------
+ * MLP weights  (replaces: nn.Linear parameter reads in Renderer_ours.forward, models.py:194-222)
+ *
+ * w[22]: device pointers in this order (PyTorch [out,in] row-major, exactly the tensors of
+ *   network_fn_state_dict):  pts_linears.{0..5}.weight/.bias interleaved (w0,b0,...,w5,b5),
+ *   pts_bias.weight, pts_bias.bias, views_linears.0.weight, .bias, feature_linear.weight, .bias,
+ *   alpha_linear.weight, .bias, rgb_linear.weight, .bias.
+ * Re-call after every optimiser step when fine-tuning (cost: one small kernel).
+ * ------------------------------------------------------------------------------------- */
+size_t mvsn_mlp_packed_bytes(int mode);
+int mvsn_mlp_pack(const float* const* w_host_array_of_device_ptrs, int mode,
+                  void* packed, size_t packed_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Layout helpers
+ *   images  [V,3,H,W] (planar, un-normalised [0,1])  ->  [V,H,W,4] (r,g,b,0) texel-interleaved
+ *   volume  [8,D,Hp,Wp] (reference layout)           ->  [D,Hp,Wp,8] channels-last
+ * The render kernel reads only the interleaved forms (one 16/32-byte sector per tap).
+ * ------------------------------------------------------------------------------------- */
+int mvsn_pack_images(const float* imgs, int V, int H, int W, float* imgs_hwc4, void* stream);
+int mvsn_volume_to_channels_last(const float* vol_cdhw, int D, int Hp, int Wp,
+                                 float* vol_dhwc, void* stream);
+int mvsn_volume_from_channels_last(const float* vol_dhwc, int D, int Hp, int Wp,
+                                   float* vol_cdhw, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Rendering  (replaces: renderer.rendering, renderer.py:138-165, and everything it calls:
+ *   gen_dir_feature :111-122, gen_pts_feats :124-136, utils.index_point_feature utils.py:357-383,
+ *   utils.build_color_volume utils.py:300-332, run_network_mvs renderer.py:42-63,
+ *   Embedder.embed models.py:47-51, Renderer_ours.forward models.py:194-222,
+ *   raw2outputs/raw2alpha renderer.py:18-26,65-92)
+ * ------------------------------------------------------------------------------------- */
+typedef struct mvsn_render_scene {
+    const float* volume_dhwc;   /* [D,Hp,Wp,8] channels-last encoding volume                    */
+    int D, Hp, Wp;
+    const float* imgs_hwc4;     /* [V,H,W,4] source images, from mvsn_pack_images               */
+    int V, H, W;                /* V must be 3 (feat_dim = 8 + 4V = 20, train_mvs_nerf_pl.py:38) */
+    const float* w2cs;          /* [V,4,4] device: world -> camera, pose_source['w2cs']           */
+    const float* intrinsics;    /* [V,3,3] device: full-resolution K, pose_source['intrinsics']   */
+    const void* mlp_packed;     /* from mvsn_mlp_pack                                             */
+    int mlp_mode;               /* MVSN_MLP_*                                                     */
+    int white_bkgd;             /* renderer.py:91-92                                              */
+} mvsn_render_scene;
+
+/* Signature-compatible entry: the caller has already run ray_marcher and get_ndc_coordinate.
+ *   rays_pts [N,S,3] world points, rays_ndc [N,S,3] volume coords in [0,1], z_vals [N,S],
+ *   rays_dir [N,3] (un-normalised).
+ * Outputs: rgb [N,3], depth [N] required; weights [N,S], alpha [N,S], input_feat [N,S,20]
+ * optional (NULL to skip).  */
+int mvsn_render_samples(const mvsn_render_scene* scene,
+                        const float* rays_pts, const float* rays_ndc, const float* z_vals,
+                        const float* rays_dir, int N, int S,
+                        float* rgb, float* depth, float* weights, float* alpha, float* input_feat,
+                        void* stream);
+
+/* Fused-caller entry: also replaces data/ray_utils.ray_marcher (data/ray_utils.py:152-197,
+ * perturb = 0) and utils.get_ndc_coordinate (utils.py:112-146) for the reference camera.
+ *   rays [N,8] = (origin, direction, near, far); t_steps [S] = linspace(0,1,S) as the caller's
+ *   framework computes it (kept as an input so z_vals match it bit for bit);
+ *   ndc_near/ndc_far: the source views' near_far; pad: cost-volume padding in feature pixels
+ *   (callers pass pad * imgScale_test); lindisp as in the reference. */
+typedef struct mvsn_ray_params {
+    float ndc_near, ndc_far;
+    float pad;
+    int lindisp;
+} mvsn_ray_params;
+
+int mvsn_render_rays(const mvsn_render_scene* scene, const mvsn_ray_params* rp,
+                     const float* rays, const float* t_steps, int N, int S,
+                     float* rgb, float* depth, float* weights, float* alpha, float* input_feat,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Cost volume  (replaces: MVSNet.build_volume_costvar_img, models.py:839-893, with
+ *   utils.homo_warp utils.py:580-630 and the F.interpolate at models.py:859)
+ *   imgs   [V,3,H,W]  ImageNet-normalised source images (H = 4h, W = 4w)
+ *   feats  [V,32,h,w] FeatureNet output
+ *   proj   [V,3,4]    src_proj @ inv(ref_proj) in feature space (row 0 unused)
+ *   depths [D]
+ * Outputs (reference layouts): cost [41,D,h+2pad,w+2pad]; in_masks [V,D,h+2pad,w+2pad] or NULL.
+ * The never-written pad border of channels 0:3 is defined as zero.
+ * workspace: mvsn_cost_volume_workspace_bytes(V,h,w) bytes.
+ * ------------------------------------------------------------------------------------- */
+size_t mvsn_cost_volume_workspace_bytes(int V, int h, int w);
+int mvsn_build_cost_volume(const float* imgs, const float* feats, const float* proj,
+                           const float* depths, int V, int H, int W, int D, int pad,
+                           float* cost, float* in_masks, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Cost regularisation  (replaces: CostRegNet.forward + ConvBnReLU3D + InPlaceABN in train mode,
+ *   models.py:674-685,725-769).
+ *   w[30]: device pointers, for each of conv0..conv6, conv7, conv9, conv11 in that order:
+ *          (conv weight, bn gamma, bn beta).  conv weight layouts as in the checkpoint:
+ *          Conv3d [Cout,Cin,3,3,3]; ConvTranspose3d [Cin,Cout,3,3,3].
+ *   cost [41,D,Hp,Wp] -> volume_dhwc [D,Hp,Wp,8] (channels-last; use
+ *   mvsn_volume_from_channels_last for the reference layout).  D, Hp, Wp must be divisible by 8.
+ *   Batch statistics are always used (every shipped caller runs MVSNet.train()).
+ * ------------------------------------------------------------------------------------- */
+size_t mvsn_costreg_workspace_bytes(int D, int Hp, int Wp);
+int mvsn_costreg_forward(const float* const* w_host_array_of_device_ptrs, const float* cost,
+                         int D, int Hp, int Wp, float* volume_dhwc,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVSNERF_B200_H */

@@ -1,0 +1,531 @@
+"""Host-side mirror of the reference's Python surface for the render hot path.
+
+Same names, argument meaning and return tuples as apchenstu/mvsnerf:
+
+    create_nerf_mvs(args, ...)                      models.py:569-654
+    MVSNet(imgs, proj_mats, near_far, pad, ...)     models.py:771-932
+    MVSNeRF / network_fn                            models.py:540-567 (Renderer_ours, :145-222)
+    RefVolume                                       models.py:935-950
+    rendering(args, pose_ref, rays_pts, ...)        renderer.py:138-165
+
+so the reference's Lightning scripts / notebooks run unchanged with
+`from mvsnerf_b200.backend import create_nerf_mvs, rendering, RefVolume`.  The modules keep the
+reference's parameter names, so `ckpts/mvsnerf-v0.tar` (and fine-tuned checkpoints) load with
+`load_state_dict(strict=True)`.  All arithmetic of the path runs in libmvsnerf_b200.so (hand
+written sm_100a CUDA, bound through ctypes); PyTorch here only owns device memory, streams and
+parameters.  There is no CPU path: CPU tensors are rejected with a RuntimeError.
+
+`render_rays` is the fused-caller entry (ray marching + NDC conversion also in the kernel) that
+replaces the notebooks' per-chunk loop of ray_marcher -> get_ndc_coordinate -> rendering.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import lib as _lib
+
+N_DEPTH_PLANES = 128     # models.py:914
+
+
+# --------------------------------------------------------------------------------------------
+# parameter containers with the reference's state_dict keys
+# --------------------------------------------------------------------------------------------
+class InPlaceABN(nn.Module):
+    """BatchNorm + leaky-ReLU(0.01) with the affine weight used as |gamma|+eps (inplace_abn).
+
+    Only used as a PyTorch op inside FeatureNet (left on cuDNN); inside CostRegNet
+    it is a parameter container and the CUDA kernels apply it."""
+
+    def __init__(self, num_features, eps=1e-5, momentum=0.1, slope=0.01):
+        super().__init__()
+        self.eps, self.momentum, self.slope = eps, momentum, slope
+        self.weight = nn.Parameter(torch.ones(num_features))
+        self.bias = nn.Parameter(torch.zeros(num_features))
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+    def forward(self, x):
+        y = F.batch_norm(x, self.running_mean, self.running_var, self.weight.abs() + self.eps, self.bias,
+                         self.training, self.momentum, self.eps)
+        return F.leaky_relu(y, self.slope)
+
+
+class ConvBnReLU(nn.Module):
+    def __init__(self, cin, cout, k=3, stride=1, pad=1):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=pad, bias=False)
+        self.bn = InPlaceABN(cout)
+
+    def forward(self, x):
+        return self.bn(self.conv(x))
+
+
+class ConvBnReLU3D(nn.Module):
+    """Parameter container (conv.weight, bn.*); evaluated by mvsn_costreg_forward."""
+
+    def __init__(self, cin, cout, stride=1):
+        super().__init__()
+        self.conv = nn.Conv3d(cin, cout, 3, stride=stride, padding=1, bias=False)
+        self.bn = InPlaceABN(cout)
+
+
+class FeatureNet(nn.Module):
+    """models.py:688-722.  Runs on cuDNN through PyTorch ("next" row 3 of SURVEY.md 8(f))."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv0 = nn.Sequential(ConvBnReLU(3, 8), ConvBnReLU(8, 8))
+        self.conv1 = nn.Sequential(ConvBnReLU(8, 16, 5, 2, 2), ConvBnReLU(16, 16), ConvBnReLU(16, 16))
+        self.conv2 = nn.Sequential(ConvBnReLU(16, 32, 5, 2, 2), ConvBnReLU(32, 32), ConvBnReLU(32, 32))
+        self.toplayer = nn.Conv2d(32, 32, 1)
+
+    def forward(self, x):
+        return self.toplayer(self.conv2(self.conv1(self.conv0(x))))
+
+
+class CostRegNet(nn.Module):
+    """models.py:725-769 parameter layout; forward = one C-ABI call."""
+
+    LAYERS = ("conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7", "conv9", "conv11")
+
+    def __init__(self, in_channels=41):
+        super().__init__()
+        self.conv0 = ConvBnReLU3D(in_channels, 8)
+        self.conv1 = ConvBnReLU3D(8, 16, stride=2)
+        self.conv2 = ConvBnReLU3D(16, 16)
+        self.conv3 = ConvBnReLU3D(16, 32, stride=2)
+        self.conv4 = ConvBnReLU3D(32, 32)
+        self.conv5 = ConvBnReLU3D(32, 64, stride=2)
+        self.conv6 = ConvBnReLU3D(64, 64)
+        for name, cin, cout in (("conv7", 64, 32), ("conv9", 32, 16), ("conv11", 16, 8)):
+            setattr(self, name, nn.Sequential(
+                nn.ConvTranspose3d(cin, cout, 3, padding=1, output_padding=1, stride=2, bias=False),
+                InPlaceABN(cout)))
+
+    def weight_list(self):
+        out = []
+        for name in self.LAYERS:
+            m = getattr(self, name)
+            conv, bn = (m.conv, m.bn) if isinstance(m, ConvBnReLU3D) else (m[0], m[1])
+            out += [conv.weight, bn.weight, bn.bias]
+        return out
+
+    def forward(self, cost):
+        """cost [1,41,D,Hp,Wp] (reference layout) -> [1,8,D,Hp,Wp] (channels-last memory)."""
+        lib = _lib.load()
+        cost = _lib.dev_f32(cost, "cost volume")
+        _, _, D, Hp, Wp = cost.shape
+        ws_bytes = lib.mvsn_costreg_workspace_bytes(D, Hp, Wp)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cost.device)
+        vol = torch.empty(D, Hp, Wp, 8, dtype=torch.float32, device=cost.device)
+        weights = [_lib.dev_f32(w.detach(), "CostRegNet weight") for w in self.weight_list()]
+        with torch.cuda.device(cost.device):
+            _lib.check(lib.mvsn_costreg_forward(_lib.ptr_array(weights), _lib.ptr(cost), D, Hp, Wp, _lib.ptr(vol),
+                                                _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "mvsn_costreg_forward")
+        return vol.permute(3, 0, 1, 2).unsqueeze(0)
+
+
+class MVSNet(nn.Module):
+    """Encoding-volume builder with the reference's call signature (models.py:771-932)."""
+
+    def __init__(self):
+        super().__init__()
+        self.feature = FeatureNet()
+        self.cost_reg_2 = CostRegNet(32 + 9)
+        self.N_importance = 0
+        self.chunk = 1024
+
+    def build_volume_costvar_img(self, imgs, feats, proj_mats, depth_values, pad=0):
+        """models.py:839-893.  imgs [1,V,3,H,W], feats [1,V,32,h,w], proj_mats [1,V,3,4], depth_values [1,D]
+        -> (img_feat [1,41,D,h',w'], in_masks [1,V,D,h',w'])."""
+        lib = _lib.load()
+        B, V, C, h, w = feats.shape
+        if B != 1:
+            raise RuntimeError("MVSNet: batch size must be 1 (as in every reference call site)")
+        H, W = imgs.shape[-2:]
+        D = depth_values.shape[-1]
+        dev = feats.device
+        imgs_c = _lib.dev_f32(imgs.reshape(V, 3, H, W), "imgs")
+        feats_c = _lib.dev_f32(feats.reshape(V, C, h, w).detach(), "feats")
+        proj_c = _lib.dev_f32(proj_mats.reshape(V, 3, 4).to(dev), "proj_mats")
+        depth_c = _lib.dev_f32(depth_values.reshape(D).to(dev), "depth_values")
+        hp, wp = h + 2 * pad, w + 2 * pad
+        cost = torch.empty(1, 41, D, hp, wp, dtype=torch.float32, device=dev)
+        masks = torch.empty(1, V, D, hp, wp, dtype=torch.float32, device=dev)
+        ws_bytes = lib.mvsn_cost_volume_workspace_bytes(V, h, w)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.mvsn_build_cost_volume(_lib.ptr(imgs_c), _lib.ptr(feats_c), _lib.ptr(proj_c),
+                                                  _lib.ptr(depth_c), V, H, W, D, int(pad), _lib.ptr(cost),
+                                                  _lib.ptr(masks), _lib.ptr(ws), ws_bytes, _lib.stream_ptr()),
+                       "mvsn_build_cost_volume")
+        return cost, masks
+
+    def forward(self, imgs, proj_mats, near_far, pad=0, return_color=False, lindisp=False):
+        if not self.training:
+            raise RuntimeError(
+                "MVSNet is in eval mode: every shipped caller of the reference runs MVSNet.train() "
+                "(batch-statistics BN, SURVEY.md F2) and the CUDA path implements exactly that; "
+                "call .train() first")
+        if not imgs.is_cuda:
+            raise RuntimeError("MVSNet: inputs must be CUDA tensors; mvsnerf_b200 has no CPU path")
+        B, V, _, H, W = imgs.shape
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # fp32 parity: no TF32 convs
+            feats = self.feature(imgs.reshape(B * V, 3, H, W))
+        feats_l = feats.view(B, V, *feats.shape[1:])
+        t = torch.linspace(0.0, 1.0, steps=N_DEPTH_PLANES, device=imgs.device, dtype=imgs.dtype)
+        near, far = near_far
+        if not lindisp:
+            depth_values = near * (1.0 - t) + far * t
+        else:
+            depth_values = 1.0 / (1.0 / near * (1.0 - t) + 1.0 / far * t)
+        depth_values = depth_values.unsqueeze(0)
+        cost, in_masks = self.build_volume_costvar_img(imgs, feats_l, proj_mats, depth_values, pad=pad)
+        if return_color:
+            feats_l = torch.cat((cost[:, :V * 3].view(B, V, 3, *cost.shape[2:]), in_masks.unsqueeze(2)), dim=2)
+        volume = self.cost_reg_2(cost)
+        return volume, feats_l, depth_values
+
+
+class _RendererV0(nn.Module):
+    """Parameter layout of Renderer_ours (models.py:145-222) for net_type 'v0'."""
+
+    def __init__(self, D=6, W=128, input_ch=63, input_ch_views=3, input_ch_feat=20, skips=(4,)):
+        super().__init__()
+        if (D, W, input_ch, input_ch_views, input_ch_feat, tuple(skips)) != (6, 128, 63, 3, 20, (4,)):
+            raise RuntimeError("the CUDA render kernel is built for the v0 network of ckpts/mvsnerf-v0.tar: "
+                               "netdepth 6, netwidth 128, 63-ch positional encoding, 3-ch view dir, 20 features")
+        self.skips = tuple(skips)
+        self.pts_linears = nn.ModuleList(
+            [nn.Linear(input_ch, W)] + [nn.Linear(W + input_ch if (i in self.skips) else W, W) for i in range(D - 1)])
+        self.pts_bias = nn.Linear(input_ch_feat, W)
+        self.views_linears = nn.ModuleList([nn.Linear(input_ch_views + W, W // 2)])
+        self.feature_linear = nn.Linear(W, W)
+        self.alpha_linear = nn.Linear(W, 1)
+        self.rgb_linear = nn.Linear(W // 2, 3)
+
+    def trunk(self, pts, feats):
+        mod = self.pts_bias(feats)
+        h = pts
+        for i, layer in enumerate(self.pts_linears):
+            h = F.relu(layer(h) * mod)
+            if i in self.skips:
+                h = torch.cat([pts, h], -1)
+        return h
+
+    def forward_alpha(self, x):
+        pts, feats = x[..., :63], x[..., 63:]
+        return torch.relu(self.alpha_linear(self.trunk(pts, feats)))
+
+    def forward(self, x):
+        pts, feats, dirs = x[..., :63], x[..., 63:83], x[..., 83:]
+        h = self.trunk(pts, feats)
+        sigma = torch.relu(self.alpha_linear(h))
+        hv = F.relu(self.views_linears[0](torch.cat([self.feature_linear(h), dirs], -1)))
+        return torch.cat([torch.sigmoid(self.rgb_linear(hv)), sigma], -1)
+
+
+class MVSNeRF(nn.Module):
+    """models.py:540-567.  `.nerf.*` parameter names as in network_fn_state_dict.  The PyTorch
+    forward below exists for the non-hot-path callers (alpha-only queries); `rendering` never uses
+    it -- it hands the parameters to the fused kernel."""
+
+    def __init__(self, D=6, W=128, input_ch_pts=63, input_ch_views=3, input_ch_feat=20, skips=(4,), net_type="v0"):
+        super().__init__()
+        if net_type != "v0":
+            raise RuntimeError(f"net_type {net_type!r}: only 'v0' (the shipped checkpoint) is implemented")
+        self.nerf = _RendererV0(D, W, input_ch_pts, input_ch_views, input_ch_feat, skips)
+        self._packed = {}
+
+    def forward(self, x):
+        return self.nerf(x)
+
+    def forward_alpha(self, x):
+        return self.nerf.forward_alpha(x)
+
+    def ordered_params(self):
+        n = self.nerf
+        out = []
+        for layer in n.pts_linears:
+            out += [layer.weight, layer.bias]
+        out += [n.pts_bias.weight, n.pts_bias.bias, n.views_linears[0].weight, n.views_linears[0].bias,
+                n.feature_linear.weight, n.feature_linear.bias, n.alpha_linear.weight, n.alpha_linear.bias,
+                n.rgb_linear.weight, n.rgb_linear.bias]
+        return out
+
+    def packed(self, mode=_lib.MLP_FP32):
+        """Kernel-layout weight image; re-packed whenever a parameter was modified in place."""
+        lib = _lib.load()
+        params = self.ordered_params()
+        dev = params[0].device
+        if not params[0].is_cuda:
+            raise RuntimeError("network_fn must live on a CUDA device; mvsnerf_b200 has no CPU path")
+        key = (mode, dev, tuple(p._version for p in params), tuple(p.data_ptr() for p in params))
+        hit = self._packed.get(mode)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        nbytes = lib.mvsn_mlp_packed_bytes(mode)
+        if nbytes == 0:
+            raise RuntimeError(f"MLP mode {mode} is not available in this build of libmvsnerf_b200")
+        buf = hit[1] if hit is not None and hit[1].numel() == nbytes and hit[1].device == dev else \
+            torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        srcs = [_lib.dev_f32(p.detach(), "MLP parameter") for p in params]
+        with torch.cuda.device(dev):
+            _lib.check(lib.mvsn_mlp_pack(_lib.ptr_array(srcs), mode, _lib.ptr(buf), nbytes, _lib.stream_ptr()),
+                       "mvsn_mlp_pack")
+        self._packed[mode] = (key, buf)
+        return buf
+
+
+class RefVolume(nn.Module):
+    """models.py:935-950: the encoding volume as a parameter (per-scene fine-tuning)."""
+
+    def __init__(self, volume):
+        super().__init__()
+        self.feat_volume = nn.Parameter(volume)
+
+    def forward(self, ray_coordinate_ref):
+        H, W = ray_coordinate_ref.shape[-3:-1]
+        grid = ray_coordinate_ref.view(-1, 1, H, W, 3).to(self.feat_volume.device) * 2 - 1.0
+        f = F.grid_sample(self.feat_volume, grid, align_corners=True, mode="bilinear")
+        return f[:, :, 0].permute(2, 3, 0, 1).squeeze()
+
+
+# --------------------------------------------------------------------------------------------
+# scene-constant device state (packed images, channels-last volume), cached per tensor version
+# --------------------------------------------------------------------------------------------
+_cache = {}
+
+
+def _cached(kind, t, build):
+    """One entry per kind, keyed on the IDENTITY of the caller's tensor object (held by weakref)
+    and its in-place version counter -- never on data_ptr, which the caching allocator recycles."""
+    hit = _cache.get(kind)
+    if hit is not None and hit[0]() is t and hit[1] == t._version:
+        return hit[2]
+    val = build()
+    _cache[kind] = (weakref.ref(t), t._version, val)
+    return val
+
+
+def clear_cache():
+    _cache.clear()
+
+
+def _volume_channels_last(volume_feature):
+    """Accepts a tensor [1,8,D,Hp,Wp] (any strides) or a RefVolume; returns ([D,Hp,Wp,8] fp32, dims)."""
+    vol = volume_feature.feat_volume if isinstance(volume_feature, nn.Module) else volume_feature
+    vol = vol.detach()
+    if vol.dim() != 5 or vol.shape[0] != 1 or vol.shape[1] != 8:
+        raise RuntimeError(f"encoding volume must be [1,8,D,H,W], got {tuple(vol.shape)}")
+    if not vol.is_cuda:
+        raise RuntimeError("encoding volume must be a CUDA tensor; mvsnerf_b200 has no CPU path")
+    _, _, D, Hp, Wp = vol.shape
+    cl = vol[0].permute(1, 2, 3, 0)
+    if vol.dtype == torch.float32 and cl.is_contiguous():
+        return cl, (D, Hp, Wp)                         # MVSNet.forward output: zero-copy
+
+    def build():
+        lib = _lib.load()
+        src = _lib.dev_f32(vol[0], "volume")
+        dst = torch.empty(D, Hp, Wp, 8, dtype=torch.float32, device=vol.device)
+        with torch.cuda.device(vol.device):
+            _lib.check(lib.mvsn_volume_to_channels_last(_lib.ptr(src), D, Hp, Wp, _lib.ptr(dst), _lib.stream_ptr()),
+                       "mvsn_volume_to_channels_last")
+        return dst
+
+    return _cached("volume", vol, build), (D, Hp, Wp)
+
+
+def _images_packed(imgs):
+    """imgs [1,V,3,H,W] un-normalised -> [V,H,W,4]."""
+    if imgs.dim() != 5 or imgs.shape[0] != 1 or imgs.shape[2] != 3:
+        raise RuntimeError(f"imgs must be [1,V,3,H,W], got {tuple(imgs.shape)}")
+    if not imgs.is_cuda:
+        raise RuntimeError("imgs must be a CUDA tensor; mvsnerf_b200 has no CPU path")
+    _, V, _, H, W = imgs.shape
+
+    def build():
+        lib = _lib.load()
+        src = _lib.dev_f32(imgs[0].detach(), "imgs")
+        dst = torch.empty(V, H, W, 4, dtype=torch.float32, device=imgs.device)
+        with torch.cuda.device(imgs.device):
+            _lib.check(lib.mvsn_pack_images(_lib.ptr(src), V, H, W, _lib.ptr(dst), _lib.stream_ptr()),
+                       "mvsn_pack_images")
+        return dst
+
+    return _cached("imgs", imgs, build), (V, H, W)
+
+
+def _make_scene(pose_ref, volume_feature, imgs, network_fn, white_bkgd, mode):
+    vol, (D, Hp, Wp) = _volume_channels_last(volume_feature)
+    im, (V, H, W) = _images_packed(imgs)
+    if V != 3:
+        raise RuntimeError(f"{V} source views: the v0 network takes exactly 3 (feat_dim = 8 + 3*4)")
+    sc = _lib.RenderScene()
+    sc.volume_dhwc, sc.D, sc.Hp, sc.Wp = vol.data_ptr(), D, Hp, Wp
+    sc.imgs_hwc4, sc.V, sc.H, sc.W = im.data_ptr(), V, H, W
+    w2cs = _lib.dev_f32(pose_ref["w2cs"].detach(), "pose_ref['w2cs']")               # [V,4,4]
+    intr = _lib.dev_f32(pose_ref["intrinsics"].detach(), "pose_ref['intrinsics']")   # [V,3,3]
+    if tuple(w2cs.shape) != (3, 4, 4) or tuple(intr.shape) != (3, 3, 3):
+        raise RuntimeError(f"pose_ref: expected w2cs [3,4,4] and intrinsics [3,3,3], got "
+                           f"{tuple(w2cs.shape)} and {tuple(intr.shape)}")
+    sc.w2cs, sc.intrinsics = w2cs.data_ptr(), intr.data_ptr()
+    packed = network_fn.packed(mode)
+    sc.mlp_packed, sc.mlp_mode, sc.white_bkgd = packed.data_ptr(), mode, int(bool(white_bkgd))
+    keep = (vol, im, packed, w2cs, intr)          # keep the device buffers alive for the duration of the call
+    return sc, keep
+
+
+DEFAULT_MLP_MODE = _lib.MLP_FP32
+
+
+def rendering(args, pose_ref, rays_pts, rays_ndc, depth_candidates, rays_o, rays_dir,
+              volume_feature=None, imgs=None, network_fn=None, img_feat=None, network_query_fn=None,
+              white_bkgd=False, **kwargs):
+    """Drop-in for renderer.rendering (renderer.py:138-165).  Returns
+    (rgb_map [N,3], input_feat [N,S,20], weights [N,S], depth_map [N], alpha [N,S], {}).
+
+    Extra keyword arguments the reference's callers pass (perturb, N_importance, network_fine,
+    use_viewdirs, raw_noise_std, NDC_local) are accepted and ignored, as the reference does.
+    `mlp_mode=` selects the GEMM arithmetic (default fp32); `want_aux=False` skips the three
+    per-sample outputs (they are returned as None)."""
+    if pose_ref is None or img_feat is not None or getattr(args, "use_color_volume", False):
+        raise RuntimeError("rendering: only the pose_ref / image-gather branch of the reference is implemented "
+                           "(use_color_volume=False, img_feat=None) -- the branch every shipped config uses")
+    mode = kwargs.pop("mlp_mode", DEFAULT_MLP_MODE)
+    want_aux = kwargs.pop("want_aux", True)
+    lib = _lib.load()
+    N, S = rays_pts.shape[:2]
+    dev = rays_pts.device
+    pts = _lib.dev_f32(rays_pts, "rays_pts")
+    ndc = _lib.dev_f32(rays_ndc, "rays_ndc")
+    z = _lib.dev_f32(depth_candidates.expand(N, S) if depth_candidates.shape != (N, S) else depth_candidates,
+                     "depth_candidates")
+    dirs = _lib.dev_f32(rays_dir, "rays_dir")
+    sc, keep = _make_scene(pose_ref, volume_feature, imgs, network_fn, white_bkgd, mode)
+    rgb = torch.empty(N, 3, dtype=torch.float32, device=dev)
+    depth = torch.empty(N, dtype=torch.float32, device=dev)
+    feat = weights = alpha = None
+    if want_aux:
+        feat = torch.empty(N, S, 20, dtype=torch.float32, device=dev)
+        weights = torch.empty(N, S, dtype=torch.float32, device=dev)
+        alpha = torch.empty(N, S, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mvsn_render_samples(C.byref(sc), _lib.ptr(pts), _lib.ptr(ndc), _lib.ptr(z), _lib.ptr(dirs),
+                                           N, S, _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(weights), _lib.ptr(alpha),
+                                           _lib.ptr(feat), _lib.stream_ptr()), "mvsn_render_samples")
+    del keep
+    return rgb, feat, weights, depth, alpha, {}
+
+
+_tsteps = {}
+
+
+def render_rays(rays, volume_feature, imgs, pose_ref, network_fn, near_far, pad, N_samples=128,
+                white_bkgd=False, lindisp=False, mlp_mode=None, out=None):
+    """Fused-caller entry: one launch renders all `rays` [N,8] = (o, d, near, far).
+
+    Replaces the notebooks' per-chunk loop `ray_marcher -> get_ndc_coordinate -> rendering`
+    (renderer_video.ipynb "DTU video rendering"; data/ray_utils.py:152-197, utils.py:112-146) with
+    perturb = 0.  `near_far` / `pad` are the arguments the reference passes to get_ndc_coordinate
+    (near_far of the source views, pad * imgScale_test).  Returns (rgb [N,3], depth [N])."""
+    lib = _lib.load()
+    mode = DEFAULT_MLP_MODE if mlp_mode is None else mlp_mode
+    rays = _lib.dev_f32(rays, "rays")
+    N = rays.shape[0]
+    dev = rays.device
+    S = int(N_samples)
+    tk = (S, dev)
+    if tk not in _tsteps:
+        _tsteps[tk] = torch.linspace(0, 1, S, device=dev)          # data/ray_utils.py:175
+    sc, keep = _make_scene(pose_ref, volume_feature, imgs, network_fn, white_bkgd, mode)
+    rp = _lib.RayParams(float(near_far[0]), float(near_far[1]), float(pad), int(bool(lindisp)))
+    if out is None:
+        rgb = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        depth = torch.empty(N, dtype=torch.float32, device=dev)
+    else:
+        rgb, depth = out
+    with torch.cuda.device(dev):
+        _lib.check(lib.mvsn_render_rays(C.byref(sc), C.byref(rp), _lib.ptr(rays), _lib.ptr(_tsteps[tk]), N, S,
+                                        _lib.ptr(rgb), _lib.ptr(depth), None, None, None, _lib.stream_ptr()),
+                   "mvsn_render_rays")
+    del keep
+    return rgb, depth
+
+
+# --------------------------------------------------------------------------------------------
+# factory (models.py:569-654)
+# --------------------------------------------------------------------------------------------
+def _embed(x, n_freqs=10):
+    """models.py:47-51 (used only by the PyTorch query function below)."""
+    freqs = 2.0 ** torch.arange(n_freqs, dtype=x.dtype, device=x.device)
+    s = (x.unsqueeze(-2) * freqs.view(-1, 1)).reshape(*x.shape[:-1], -1)
+    return torch.cat([x, torch.sin(s), torch.cos(s)], -1)
+
+
+def _network_query(pts, viewdirs, rays_feats, network_fn, netchunk=1024):
+    """run_network_mvs (renderer.py:42-63) for the callers outside `rendering` (alpha-only queries)."""
+    x = _embed(pts)
+    if rays_feats is not None:
+        x = torch.cat([x, rays_feats], -1)
+    if viewdirs is not None:
+        if viewdirs.dim() != 3:
+            viewdirs = viewdirs[:, None].expand(-1, x.shape[1], -1)
+        x = torch.cat([x, viewdirs], -1)
+    fn = network_fn.forward_alpha if viewdirs is None else network_fn
+    return torch.cat([fn(x[i:i + netchunk]) for i in range(0, x.shape[0], netchunk)], 0)
+
+
+def create_nerf_mvs(args, pts_embedder=True, use_mvs=False, dir_embedder=True, device=None):
+    """Same contract as models.create_nerf_mvs: returns
+    (render_kwargs_train, render_kwargs_test, start, grad_vars)."""
+    if not pts_embedder or dir_embedder:
+        raise RuntimeError("create_nerf_mvs: the fused kernel implements pts_embedder=True, dir_embedder=False "
+                           "(the combination every shipped caller uses)")
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("create_nerf_mvs: no CUDA device; mvsnerf_b200 has no CPU path")
+        device = torch.device("cuda", torch.cuda.current_device())
+    model = MVSNeRF(D=args.netdepth, W=args.netwidth, input_ch_pts=args.pts_dim * (1 + 2 * args.multires),
+                    input_ch_views=args.dir_dim, input_ch_feat=args.feat_dim, net_type=args.net_type).to(device)
+    grad_vars = list(model.parameters())
+    if getattr(args, "N_importance", 0) > 0:
+        raise RuntimeError("N_importance > 0 (hierarchical sampling) is outside the hot path (SURVEY.md 2.1)")
+    encoding_net = None
+    if use_mvs:
+        encoding_net = MVSNet().to(device)
+        grad_vars += list(encoding_net.parameters())
+    ckpt_path = getattr(args, "ckpt", None)
+    if ckpt_path is not None and ckpt_path != "None":
+        ckpt = torch.load(ckpt_path, map_location=device, weights_only=False)
+        if use_mvs:
+            encoding_net.load_state_dict(ckpt["network_mvs_state_dict"])
+        model.load_state_dict(ckpt["network_fn_state_dict"])
+    render_kwargs_train = {
+        "network_query_fn": lambda pts, viewdirs, rays_feats, network_fn: _network_query(
+            pts, viewdirs, rays_feats, network_fn, args.netchunk),
+        "perturb": args.perturb, "N_importance": args.N_importance, "network_fine": None,
+        "N_samples": args.N_samples, "network_fn": model, "network_mvs": encoding_net,
+        "use_viewdirs": args.use_viewdirs, "white_bkgd": args.white_bkgd, "raw_noise_std": args.raw_noise_std,
+    }
+    render_kwargs_test = dict(render_kwargs_train)
+    render_kwargs_test["perturb"] = False
+    return render_kwargs_train, render_kwargs_test, 0, grad_vars
+
+
+def load_weights_npz(model_fn: MVSNeRF | None, model_mvs: MVSNet | None, path: str):
+    """Load the `mlp/` and `mvs/` tensors of tests/golden/mvsnerf_v0_weights.npz (an export of
+    ckpts/mvsnerf-v0.tar that travels with the repository)."""
+    import numpy as np
+    z = np.load(path)
+    if model_fn is not None:
+        model_fn.load_state_dict({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("mlp/")})
+    if model_mvs is not None:
+        model_mvs.load_state_dict({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("mvs/")})

@@ -1,0 +1,242 @@
+// C-ABI entry points (include/mvsnerf_b200.h): argument checking, layout helpers, weight
+// packing and the render dispatch.  Kernels live in the sibling .cu files.
+#include "render_frontend.cuh"
+
+namespace mvsn {
+
+// ------------------------------------------------------------------------------------------
+// error channel
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    static int cache[64] = {0};
+    if (dev < 64 && cache[dev]) return cache[dev];
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev < 64) cache[dev] = n;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
+// layout kernels
+// ------------------------------------------------------------------------------------------
+__global__ void pack_images_kernel(const float* __restrict__ src, float4* __restrict__ dst, int V, int HW) {
+    const long long n = (long long)V * HW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i / HW), p = (int)(i - (long long)v * HW);
+        const float* s = src + (size_t)v * 3 * HW + p;
+        dst[i] = make_float4(s[0], s[HW], s[2 * (size_t)HW], 0.f);
+    }
+}
+
+// [8][nvox] <-> [nvox][8]
+__global__ void vol_to_cl_kernel(const float* __restrict__ src, float4* __restrict__ dst, long long nvox) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox; i += (long long)gridDim.x * blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = __ldg(src + c * nvox + i);
+        dst[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+__global__ void vol_from_cl_kernel(const float4* __restrict__ src, float* __restrict__ dst, long long nvox) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox; i += (long long)gridDim.x * blockDim.x) {
+        float4 a = __ldg(src + 2 * i), b = __ldg(src + 2 * i + 1);
+        dst[0 * nvox + i] = a.x; dst[1 * nvox + i] = a.y; dst[2 * nvox + i] = a.z; dst[3 * nvox + i] = a.w;
+        dst[4 * nvox + i] = b.x; dst[5 * nvox + i] = b.y; dst[6 * nvox + i] = b.z; dst[7 * nvox + i] = b.w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 MLP weight image
+// ------------------------------------------------------------------------------------------
+struct MlpPtrs { const float* p[MVSN_N_MLP_TENSORS]; };
+// indices into the 22-tensor array (see header)
+enum { I_W0 = 0, I_B0 = 1, I_WB = 12, I_BB = 13, I_WV = 14, I_BV = 15, I_WF = 16, I_BF = 17,
+       I_WA = 18, I_BA = 19, I_WR = 20, I_BR = 21 };
+
+// dst[k][n] (ld = ldn) = src[n][src_col0 + k] for k < kreal, 0 for kreal <= k < kpad
+__device__ void transpose_into(float* dst, int ldn, int nout, int kpad, const float* src, int src_ld,
+                               int src_col0, int kreal, int tid, int nthreads) {
+    for (int i = tid; i < kpad * nout; i += nthreads) {
+        const int k = i / nout, n = i - k * nout;
+        dst[k * ldn + n] = k < kreal ? src[(size_t)n * src_ld + src_col0 + k] : 0.f;
+    }
+}
+__device__ void copy_into(float* dst, const float* src, int n, int npad, int tid, int nthreads) {
+    for (int i = tid; i < npad; i += nthreads) dst[i] = i < n ? src[i] : 0.f;
+}
+
+__global__ void pack_mlp_fp32_kernel(MlpPtrs w, float* __restrict__ out) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    using namespace w32;
+    transpose_into(out + WB, 128, 128, 32, w.p[I_WB], 20, 0, 20, tid, nt);
+    copy_into(out + BB, w.p[I_BB], 128, 128, tid, nt);
+    transpose_into(out + W0, 128, 128, 64, w.p[I_W0], 63, 0, 63, tid, nt);
+    copy_into(out + B0, w.p[I_B0], 128, 128, tid, nt);
+    for (int l = 1; l <= 4; ++l) {
+        transpose_into(out + W1 + (l - 1) * LSTR, 128, 128, 128, w.p[2 * l], 128, 0, 128, tid, nt);
+        copy_into(out + W1 + (l - 1) * LSTR + 128 * 128, w.p[2 * l + 1], 128, 128, tid, nt);
+    }
+    transpose_into(out + W5, 128, 128, 64, w.p[10], 191, 0, 63, tid, nt);             // pe part
+    transpose_into(out + W5 + 64 * 128, 128, 128, 128, w.p[10], 191, 63, 128, tid, nt); // h part
+    copy_into(out + B5, w.p[11], 128, 128, tid, nt);
+    copy_into(out + WA, w.p[I_WA], 128, 128, tid, nt);
+    copy_into(out + BA, w.p[I_BA], 1, 4, tid, nt);
+    transpose_into(out + WF, 128, 128, 128, w.p[I_WF], 128, 0, 128, tid, nt);
+    copy_into(out + BF, w.p[I_BF], 128, 128, tid, nt);
+    transpose_into(out + WV, 64, 64, 128, w.p[I_WV], 131, 0, 128, tid, nt);
+    transpose_into(out + WVD, 64, 64, 4, w.p[I_WV], 131, 128, 3, tid, nt);
+    copy_into(out + BV, w.p[I_BV], 64, 64, tid, nt);
+    // rgb_linear [3][64] is used row-wise (dot products), no transpose
+    for (int i = tid; i < 4 * 64; i += nt) out[WR + i] = i < 3 * 64 ? w.p[I_WR][i] : 0.f;
+    copy_into(out + BR, w.p[I_BR], 3, 4, tid, nt);
+}
+
+static int make_scene(const mvsn_render_scene* s, SceneDev& d) {
+    MVSN_REQUIRE(s != nullptr, MVSN_ENULL, "scene is NULL");
+    MVSN_REQUIRE(s->volume_dhwc && s->imgs_hwc4 && s->mlp_packed, MVSN_ENULL, "scene has a NULL buffer");
+    MVSN_REQUIRE(s->V == 3, MVSN_EBADSHAPE, "V=%d: the v0 MLP takes 8 + 4*3 feature channels", s->V);
+    MVSN_REQUIRE(s->D > 0 && s->Hp > 0 && s->Wp > 0 && s->H > 1 && s->W > 1, MVSN_EBADSHAPE, "bad scene dims");
+    MVSN_REQUIRE(aligned16(s->volume_dhwc) && aligned16(s->imgs_hwc4) && aligned16(s->mlp_packed), MVSN_EALIGN,
+                 "scene buffers must be 16-byte aligned");
+    d.vol = s->volume_dhwc; d.imgs = reinterpret_cast<const float4*>(s->imgs_hwc4);
+    d.D = s->D; d.Hp = s->Hp; d.Wp = s->Wp; d.V = s->V; d.H = s->H; d.W = s->W;
+    MVSN_REQUIRE(s->w2cs && s->intrinsics, MVSN_ENULL, "scene camera pointers are NULL");
+    d.w2cs = s->w2cs; d.intrinsics = s->intrinsics;
+    d.white_bkgd = s->white_bkgd;
+    return MVSN_OK;
+}
+
+static int dispatch_render(const mvsn_render_scene* scene, const SceneDev& sc, const RenderIO& io, bool fast,
+                           cudaStream_t stream) {
+    switch (scene->mlp_mode) {
+        case MVSN_MLP_FP32:
+            return launch_render_fp32(sc, io, fast, static_cast<const float*>(scene->mlp_packed), stream);
+        default:
+            set_error("mlp_mode %d is not available in this build", scene->mlp_mode);
+            return MVSN_EUNSUPPORTED;
+    }
+}
+
+}  // namespace mvsn
+
+using namespace mvsn;
+
+extern "C" {
+
+const char* mvsn_last_error(void) { return g_err; }
+int mvsn_abi_version(void) { return 1; }
+
+size_t mvsn_mlp_packed_bytes(int mode) {
+    switch (mode) {
+        case MVSN_MLP_FP32: return (size_t)w32::TOTAL * sizeof(float);
+        default: return 0;
+    }
+}
+
+int mvsn_mlp_pack(const float* const* w, int mode, void* packed, size_t packed_bytes, void* stream) {
+    MVSN_REQUIRE(w && packed, MVSN_ENULL, "mvsn_mlp_pack: NULL argument");
+    const size_t need = mvsn_mlp_packed_bytes(mode);
+    MVSN_REQUIRE(need != 0, MVSN_EUNSUPPORTED, "mvsn_mlp_pack: mode %d not available", mode);
+    MVSN_REQUIRE(packed_bytes >= need, MVSN_EWORKSPACE, "mvsn_mlp_pack: need %zu bytes, got %zu", need, packed_bytes);
+    MVSN_REQUIRE(aligned16(packed), MVSN_EALIGN, "mvsn_mlp_pack: packed buffer must be 16-byte aligned");
+    MlpPtrs p;
+    for (int i = 0; i < MVSN_N_MLP_TENSORS; ++i) {
+        MVSN_REQUIRE(w[i] != nullptr, MVSN_ENULL, "mvsn_mlp_pack: tensor %d is NULL", i);
+        p.p[i] = w[i];
+    }
+    pack_mlp_fp32_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(p, static_cast<float*>(packed));
+    MVSN_CUDA_CHECK(cudaGetLastError());
+    return MVSN_OK;
+}
+
+int mvsn_pack_images(const float* imgs, int V, int H, int W, float* out, void* stream) {
+    MVSN_REQUIRE(imgs && out, MVSN_ENULL, "mvsn_pack_images: NULL argument");
+    MVSN_REQUIRE(V > 0 && H > 0 && W > 0, MVSN_EBADSHAPE, "mvsn_pack_images: bad shape");
+    MVSN_REQUIRE(aligned16(out), MVSN_EALIGN, "mvsn_pack_images: output must be 16-byte aligned");
+    const long long n = (long long)V * H * W;
+    pack_images_kernel<<<cdiv(n, 256) < 4096 ? cdiv(n, 256) : 4096, 256, 0, (cudaStream_t)stream>>>(
+        imgs, reinterpret_cast<float4*>(out), V, H * W);
+    MVSN_CUDA_CHECK(cudaGetLastError());
+    return MVSN_OK;
+}
+
+int mvsn_volume_to_channels_last(const float* src, int D, int Hp, int Wp, float* dst, void* stream) {
+    MVSN_REQUIRE(src && dst, MVSN_ENULL, "mvsn_volume_to_channels_last: NULL argument");
+    MVSN_REQUIRE(aligned16(dst), MVSN_EALIGN, "mvsn_volume_to_channels_last: output must be 16-byte aligned");
+    const long long n = (long long)D * Hp * Wp;
+    MVSN_REQUIRE(n > 0, MVSN_EBADSHAPE, "mvsn_volume_to_channels_last: bad shape");
+    vol_to_cl_kernel<<<cdiv(n, 256) < 8192 ? cdiv(n, 256) : 8192, 256, 0, (cudaStream_t)stream>>>(
+        src, reinterpret_cast<float4*>(dst), n);
+    MVSN_CUDA_CHECK(cudaGetLastError());
+    return MVSN_OK;
+}
+
+int mvsn_volume_from_channels_last(const float* src, int D, int Hp, int Wp, float* dst, void* stream) {
+    MVSN_REQUIRE(src && dst, MVSN_ENULL, "mvsn_volume_from_channels_last: NULL argument");
+    MVSN_REQUIRE(aligned16(src), MVSN_EALIGN, "mvsn_volume_from_channels_last: input must be 16-byte aligned");
+    const long long n = (long long)D * Hp * Wp;
+    MVSN_REQUIRE(n > 0, MVSN_EBADSHAPE, "mvsn_volume_from_channels_last: bad shape");
+    vol_from_cl_kernel<<<cdiv(n, 256) < 8192 ? cdiv(n, 256) : 8192, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(src), dst, n);
+    MVSN_CUDA_CHECK(cudaGetLastError());
+    return MVSN_OK;
+}
+
+int mvsn_render_samples(const mvsn_render_scene* scene, const float* rays_pts, const float* rays_ndc,
+                        const float* z_vals, const float* rays_dir, int N, int S, float* rgb, float* depth,
+                        float* weights, float* alpha, float* input_feat, void* stream) {
+    SceneDev sc;
+    int rc = make_scene(scene, sc);
+    if (rc) return rc;
+    MVSN_REQUIRE(N >= 0 && S > 0, MVSN_EBADSHAPE, "mvsn_render_samples: N=%d S=%d", N, S);
+    if (N == 0) return MVSN_OK;
+    MVSN_REQUIRE(rays_pts && rays_ndc && z_vals && rays_dir && rgb && depth, MVSN_ENULL,
+                 "mvsn_render_samples: NULL required pointer");
+    MVSN_REQUIRE(!input_feat || aligned16(input_feat), MVSN_EALIGN, "input_feat must be 16-byte aligned");
+    RenderIO io{};
+    io.pts = rays_pts; io.ndc = rays_ndc; io.z = z_vals; io.dirs = rays_dir;
+    io.N = N; io.S = S;
+    io.rgb = rgb; io.depth = depth; io.weights = weights; io.alpha = alpha; io.input_feat = input_feat;
+    return dispatch_render(scene, sc, io, false, (cudaStream_t)stream);
+}
+
+int mvsn_render_rays(const mvsn_render_scene* scene, const mvsn_ray_params* rp, const float* rays,
+                     const float* t_steps, int N, int S, float* rgb, float* depth, float* weights,
+                     float* alpha, float* input_feat, void* stream) {
+    SceneDev sc;
+    int rc = make_scene(scene, sc);
+    if (rc) return rc;
+    MVSN_REQUIRE(rp != nullptr, MVSN_ENULL, "mvsn_render_rays: ray params NULL");
+    MVSN_REQUIRE(N >= 0 && S > 0, MVSN_EBADSHAPE, "mvsn_render_rays: N=%d S=%d", N, S);
+    if (N == 0) return MVSN_OK;
+    MVSN_REQUIRE(rays && t_steps && rgb && depth, MVSN_ENULL, "mvsn_render_rays: NULL required pointer");
+    MVSN_REQUIRE(aligned16(rays), MVSN_EALIGN, "rays must be 16-byte aligned");
+    MVSN_REQUIRE(!input_feat || aligned16(input_feat), MVSN_EALIGN, "input_feat must be 16-byte aligned");
+    RenderIO io{};
+    io.rays = rays; io.t_steps = t_steps;
+    io.N = N; io.S = S;
+    io.rgb = rgb; io.depth = depth; io.weights = weights; io.alpha = alpha; io.input_feat = input_feat;
+    // host-side scalars exactly as utils.get_ndc_coordinate forms them (python floats -> fp32)
+    io.rg.near = rp->ndc_near;
+    io.rg.far_minus_near = (float)((double)rp->ndc_far - (double)rp->ndc_near);
+    io.rg.inv_near = (float)(1.0 / (double)rp->ndc_near);
+    io.rg.inv_far_minus_inv_near = (float)(1.0 / (double)rp->ndc_far - 1.0 / (double)rp->ndc_near);
+    io.rg.pad = rp->pad;
+    io.rg.wf = (float)scene->W / 4.0f;     // (inv_scale + 1) / 4, utils.py:139
+    io.rg.hf = (float)scene->H / 4.0f;
+    io.rg.lindisp = rp->lindisp;
+    return dispatch_render(scene, sc, io, true, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,441 @@
+// K-B: CostRegNet (models.py:725-769) -- ten bias-free 3x3x3 (transposed) convolutions, each
+// followed by InPlaceABN in TRAIN mode (batch statistics, |gamma|+eps, leaky-ReLU 0.01).
+//
+// Train-mode BN makes every layer end in a grid-wide per-channel reduction, so a layer is one
+// kernel that (a) applies the PREVIOUS layer's normalisation + activation while loading its input
+// ("normalise on load": activations are stored raw, exactly once), (b) convolves, (c) stores the
+// raw result and (d) accumulates per-channel sum / sum of squares (fp32 per CTA, fp64 across CTAs)
+// for the NEXT layer's load.  No separate BN or activation pass over any tensor exists, and the
+// U-Net skip additions are folded into the consumer's load as a second (tensor, statistics) pair.
+//
+// Thread mapping: a thread owns a strip of 4 consecutive output voxels along x for CT output
+// channels; a warp owns 32 consecutive strips, so input rows are fetched with one 16-byte load per
+// lane and the +-1 halo comes from the neighbouring lanes by shuffle.  Weights for the CTA's CT
+// output channels sit in shared memory ([cin][27][CT], read as broadcast LDS.128).
+#include "common.cuh"
+
+namespace mvsn {
+
+constexpr float kBnEps = 1e-5f;
+constexpr float kSlope = 0.01f;
+constexpr int kMaxCin = 64;
+
+struct ActSrc {                 // one input tensor of a layer, stored raw + its batch statistics
+    const float* x;             // [C][D][H][W]
+    const double* stats;        // [C][2] sum, sum of squares over `count` voxels; null = plain tensor
+    const float* gamma;         // [C]
+    const float* beta;          // [C]
+    double count;
+};
+
+struct ConvArgs {
+    ActSrc in0, in1;            // in1.x == null unless the layer input is a skip sum
+    int Cin, Din, Hin, Win;
+    const float* w;             // Conv3d [Cout][Cin][27] or ConvTranspose3d [Cin][Cout][27]
+    int Cout, Dout, Hout, Wout;
+    float* out;                 // [Cout][Dout][Hout][Wout] raw
+    double* stats_out;          // [Cout][2]
+};
+
+__device__ __forceinline__ float act(float x, float sc, float sh) {
+    const float y = fmaf(x, sc, sh);
+    return y > 0.f ? y : y * kSlope;
+}
+
+// per-channel (scale, shift) of a source: y = leaky(x * scale + shift)
+__device__ void load_norm(const ActSrc& s, int C, float* sc, float* sh, int tid, int nthreads) {
+    for (int c = tid; c < C; c += nthreads) {
+        if (s.stats) {
+            const double mean = s.stats[2 * c] / s.count;
+            double var = s.stats[2 * c + 1] / s.count - mean * mean;     // biased, as F.batch_norm(training=True)
+            var = var > 0.0 ? var : 0.0;
+            const double inv = 1.0 / sqrt(var + (double)kBnEps);
+            const double g = fabs((double)s.gamma[c]) + (double)kBnEps;
+            sc[c] = (float)(g * inv);
+            sh[c] = (float)((double)s.beta[c] - mean * g * inv);
+        } else {
+            sc[c] = 1.f; sh[c] = 0.f;
+        }
+    }
+}
+
+template <bool IDENT>   // IDENT: plain tensor (the cost volume), no normalisation / activation
+__device__ __forceinline__ float4 load_row4(const float* __restrict__ row, int x, int W, bool row_ok, bool vec,
+                                            float sc, float sh) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row_ok) {
+        if (vec && x + 3 < W) {
+            v = __ldg(reinterpret_cast<const float4*>(row + x));
+            if (!IDENT) { v.x = act(v.x, sc, sh); v.y = act(v.y, sc, sh); v.z = act(v.z, sc, sh); v.w = act(v.w, sc, sh); }
+        } else {
+            if (x < W)     v.x = IDENT ? __ldg(row + x)     : act(__ldg(row + x), sc, sh);
+            if (x + 1 < W) v.y = IDENT ? __ldg(row + x + 1) : act(__ldg(row + x + 1), sc, sh);
+            if (x + 2 < W) v.z = IDENT ? __ldg(row + x + 2) : act(__ldg(row + x + 2), sc, sh);
+            if (x + 3 < W) v.w = IDENT ? __ldg(row + x + 3) : act(__ldg(row + x + 3), sc, sh);
+        }
+    }
+    return v;
+}
+
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// write 4 x CT raw outputs + accumulate batch statistics
+template <int CT>
+__device__ __forceinline__ void store_and_stats(const ConvArgs& a, float (&acc)[4][CT], bool active, int z, int y,
+                                                int x0, int cg, float* s_stat, int tid) {
+    const int lane = tid & 31;
+    const size_t plane = (size_t)a.Hout * a.Wout, vol = plane * a.Dout;
+    const bool vec = (a.Wout & 3) == 0;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+        float s = 0.f, q = 0.f;
+        if (active) {
+            float* o = a.out + (size_t)(cg * CT + c) * vol + (size_t)z * plane + (size_t)y * a.Wout + x0;
+            if (vec) {
+                *reinterpret_cast<float4*>(o) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { s += acc[i][c]; q = fmaf(acc[i][c], acc[i][c], q); }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (x0 + i < a.Wout) { o[i] = acc[i][c]; s += acc[i][c]; q = fmaf(acc[i][c], acc[i][c], q); }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, off);
+            q += __shfl_xor_sync(0xffffffffu, q, off);
+        }
+        if (lane == 0) { atomicAdd(&s_stat[2 * c], s); atomicAdd(&s_stat[2 * c + 1], q); }
+    }
+    __syncthreads();
+    if (tid < 2 * CT) atomicAdd(&a.stats_out[2 * (cg * CT) + tid], (double)s_stat[tid]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Conv3d k3 p1, stride 1 or 2
+// ------------------------------------------------------------------------------------------
+template <int CT, int STRIDE, bool IDENT>
+__global__ void __launch_bounds__(128)
+conv3d_k3_kernel(const ConvArgs a) {
+    extern __shared__ __align__(16) float s_w[];            // [Cin][27][CT]
+    __shared__ float s_sc[2][kMaxCin], s_sh[2][kMaxCin];
+    __shared__ float s_stat[2 * CT];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cg = blockIdx.y;
+    const bool dual = a.in1.x != nullptr;
+
+    for (int i = tid; i < a.Cin * 27 * CT; i += 128) {
+        const int c = i % CT, r = i / CT;                   // r = ci*27 + tap
+        s_w[i] = __ldg(a.w + (size_t)(cg * CT + c) * a.Cin * 27 + r);
+    }
+    if (!IDENT) {
+        load_norm(a.in0, a.Cin, s_sc[0], s_sh[0], tid, 128);
+        if (dual) load_norm(a.in1, a.Cin, s_sc[1], s_sh[1], tid, 128);
+    }
+    if (tid < 2 * CT) s_stat[tid] = 0.f;
+    __syncthreads();
+
+    const int nsx = (a.Wout + 3) >> 2;
+    const long long nstrips = (long long)a.Dout * a.Hout * nsx;
+    const long long sid = (long long)blockIdx.x * 128 + tid;
+    const bool active = sid < nstrips;
+    int z = 0, y = 0, sx = 0;
+    if (active) { sx = (int)(sid % nsx); long long r = sid / nsx; y = (int)(r % a.Hout); z = (int)(r / a.Hout); }
+    const int x0 = sx * 4;                                   // first output x
+    const int xin = x0 * STRIDE;                             // first centre input x
+    const bool vec = (a.Win & 3) == 0;
+    const size_t iplane = (size_t)a.Hin * a.Win, ivol = iplane * a.Din;
+
+    float acc[4][CT];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < CT; ++c) acc[i][c] = 0.f;
+
+    for (int ci = 0; ci < a.Cin; ++ci) {
+        const float sc0 = IDENT ? 1.f : s_sc[0][ci], sh0 = IDENT ? 0.f : s_sh[0][ci];
+        const float sc1 = dual ? s_sc[1][ci] : 1.f, sh1 = dual ? s_sh[1][ci] : 0.f;
+        const float* base0 = a.in0.x + (size_t)ci * ivol;
+        const float* base1 = dual ? a.in1.x + (size_t)ci * ivol : nullptr;
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz) {
+            const int zi = z * STRIDE - 1 + dz;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const int yi = y * STRIDE - 1 + dy;
+                const bool row_ok = active && (unsigned)zi < (unsigned)a.Din && (unsigned)yi < (unsigned)a.Hin;
+                const size_t roff = (size_t)zi * iplane + (size_t)yi * a.Win;
+                // v[0] = input at xin-1, v[1..] = inputs at xin, xin+1, ...
+                float v[STRIDE == 1 ? 6 : 9];
+                float4 c0 = load_row4<IDENT>(base0 + roff, xin, a.Win, row_ok, vec, sc0, sh0);
+                if (dual) c0 = add4(c0, load_row4<false>(base1 + roff, xin, a.Win, row_ok, vec, sc1, sh1));
+                v[1] = c0.x; v[2] = c0.y; v[3] = c0.z; v[4] = c0.w;
+                float last = c0.w;
+                if (STRIDE == 2) {
+                    float4 c1 = load_row4<IDENT>(base0 + roff, xin + 4, a.Win, row_ok, vec, sc0, sh0);
+                    if (dual) c1 = add4(c1, load_row4<false>(base1 + roff, xin + 4, a.Win, row_ok, vec, sc1, sh1));
+                    v[5] = c1.x; v[6] = c1.y; v[7] = c1.z; v[8] = c1.w;
+                    last = c1.w;
+                }
+                // halo from the neighbouring strips (same row when sx > 0 / sx < nsx-1)
+                float left = __shfl_up_sync(0xffffffffu, last, 1);
+                if (sx == 0) left = 0.f;
+                else if (lane == 0) {
+                    left = 0.f;
+                    if (row_ok) {
+                        left = IDENT ? __ldg(base0 + roff + xin - 1) : act(__ldg(base0 + roff + xin - 1), sc0, sh0);
+                        if (dual) left += act(__ldg(base1 + roff + xin - 1), sc1, sh1);
+                    }
+                }
+                v[0] = left;
+                if (STRIDE == 1) {
+                    float right = __shfl_down_sync(0xffffffffu, c0.x, 1);
+                    if (sx == nsx - 1) right = 0.f;
+                    else if (lane == 31) {
+                        right = 0.f;
+                        if (row_ok && xin + 4 < a.Win) {
+                            right = IDENT ? __ldg(base0 + roff + xin + 4) : act(__ldg(base0 + roff + xin + 4), sc0, sh0);
+                            if (dual) right += act(__ldg(base1 + roff + xin + 4), sc1, sh1);
+                        }
+                    }
+                    v[5] = right;
+                }
+                const float* wrow = s_w + ((ci * 27) + dz * 9 + dy * 3) * CT;
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    float wv[CT];
+#pragma unroll
+                    for (int c4 = 0; c4 < CT / 4; ++c4) {
+                        const float4 t = *reinterpret_cast<const float4*>(wrow + dx * CT + c4 * 4);
+                        wv[c4 * 4] = t.x; wv[c4 * 4 + 1] = t.y; wv[c4 * 4 + 2] = t.z; wv[c4 * 4 + 3] = t.w;
+                    }
+#pragma unroll
+                    for (int o = 0; o < 4; ++o) {
+                        const float in = v[o * STRIDE + dx];
+#pragma unroll
+                        for (int c = 0; c < CT; ++c) acc[o][c] = fmaf(in, wv[c], acc[o][c]);
+                    }
+                }
+            }
+        }
+    }
+    store_and_stats<CT>(a, acc, active, z, y, x0, cg, s_stat, tid);
+}
+
+// ------------------------------------------------------------------------------------------
+// ConvTranspose3d k3 s2 p1 output_padding 1:  out[o] += in[i] * W[k],  o = 2 i - 1 + k
+//   even o: (k=1, i=o/2);  odd o: (k=0, i=(o+1)/2) and (k=2, i=(o-1)/2)
+// A strip of 4 outputs starting at x0 = 4 sx reads inputs ix = 2 sx, 2 sx + 1, 2 sx + 2.
+// ------------------------------------------------------------------------------------------
+template <int CT>
+__global__ void __launch_bounds__(128)
+deconv3d_k3s2_kernel(const ConvArgs a) {
+    extern __shared__ __align__(16) float s_w[];            // [Cin][27][CT]
+    __shared__ float s_sc[2][kMaxCin], s_sh[2][kMaxCin];
+    __shared__ float s_stat[2 * CT];
+    const int tid = threadIdx.x;
+    const int cg = blockIdx.y;
+    const bool dual = a.in1.x != nullptr;
+
+    for (int i = tid; i < a.Cin * 27 * CT; i += 128) {
+        const int c = i % CT, r = i / CT, ci = r / 27, tap = r - ci * 27;
+        s_w[i] = __ldg(a.w + ((size_t)ci * a.Cout + cg * CT + c) * 27 + tap);
+    }
+    load_norm(a.in0, a.Cin, s_sc[0], s_sh[0], tid, 128);
+    if (dual) load_norm(a.in1, a.Cin, s_sc[1], s_sh[1], tid, 128);
+    if (tid < 2 * CT) s_stat[tid] = 0.f;
+    __syncthreads();
+
+    const int nsx = (a.Wout + 3) >> 2;
+    const long long nstrips = (long long)a.Dout * a.Hout * nsx;
+    const long long sid = (long long)blockIdx.x * 128 + tid;
+    const bool active = sid < nstrips;
+    int z = 0, y = 0, sx = 0;
+    if (active) { sx = (int)(sid % nsx); long long r = sid / nsx; y = (int)(r % a.Hout); z = (int)(r / a.Hout); }
+    const int x0 = sx * 4, xi0 = sx * 2;
+    const size_t iplane = (size_t)a.Hin * a.Win, ivol = iplane * a.Din;
+
+    // (k, i) pairs along z and y for this output row
+    int kz[2], iz[2], nz, ky[2], iy[2], ny;
+    if ((z & 1) == 0) { nz = 1; kz[0] = 1; iz[0] = z >> 1; kz[1] = 0; iz[1] = 0; }
+    else { nz = 2; kz[0] = 0; iz[0] = (z + 1) >> 1; kz[1] = 2; iz[1] = (z - 1) >> 1; }
+    if ((y & 1) == 0) { ny = 1; ky[0] = 1; iy[0] = y >> 1; ky[1] = 0; iy[1] = 0; }
+    else { ny = 2; ky[0] = 0; iy[0] = (y + 1) >> 1; ky[1] = 2; iy[1] = (y - 1) >> 1; }
+
+    float acc[4][CT];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < CT; ++c) acc[i][c] = 0.f;
+
+    if (active) {
+        for (int ci = 0; ci < a.Cin; ++ci) {
+            const float sc0 = s_sc[0][ci], sh0 = s_sh[0][ci];
+            const float sc1 = dual ? s_sc[1][ci] : 1.f, sh1 = dual ? s_sh[1][ci] : 0.f;
+            const float* base0 = a.in0.x + (size_t)ci * ivol;
+            const float* base1 = dual ? a.in1.x + (size_t)ci * ivol : nullptr;
+            for (int jz = 0; jz < nz; ++jz) {
+                if (iz[jz] >= a.Din) continue;
+                for (int jy = 0; jy < ny; ++jy) {
+                    if (iy[jy] >= a.Hin) continue;
+                    const size_t roff = (size_t)iz[jz] * iplane + (size_t)iy[jy] * a.Win;
+                    float v[3];
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        v[i] = 0.f;
+                        if (xi0 + i < a.Win) {
+                            v[i] = act(__ldg(base0 + roff + xi0 + i), sc0, sh0);
+                            if (dual) v[i] += act(__ldg(base1 + roff + xi0 + i), sc1, sh1);
+                        }
+                    }
+                    const float* wrow = s_w + ((ci * 27) + kz[jz] * 9 + ky[jy] * 3) * CT;
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) {
+                        const float w0 = wrow[c], w1 = wrow[CT + c], w2 = wrow[2 * CT + c];
+                        acc[0][c] = fmaf(v[0], w1, acc[0][c]);                               // x0   : k=1, i=xi0
+                        acc[1][c] = fmaf(v[1], w0, fmaf(v[0], w2, acc[1][c]));               // x0+1 : k=0,i=xi0+1 ; k=2,i=xi0
+                        acc[2][c] = fmaf(v[1], w1, acc[2][c]);                               // x0+2 : k=1, i=xi0+1
+                        acc[3][c] = fmaf(v[2], w0, fmaf(v[1], w2, acc[3][c]));               // x0+3 : k=0,i=xi0+2 ; k=2,i=xi0+1
+                    }
+                }
+            }
+        }
+    }
+    store_and_stats<CT>(a, acc, active, z, y, x0, cg, s_stat, tid);
+}
+
+// ------------------------------------------------------------------------------------------
+// final: volume = ABN(conv0) + ABN(deconv11)  -> channels-last [nvox][8]   (models.py:766)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+finalize_volume_kernel(ActSrc s0, ActSrc s1, long long nvox, float4* __restrict__ out) {
+    __shared__ float sc[2][8], sh[2][8];
+    load_norm(s0, 8, sc[0], sh[0], threadIdx.x, 256);
+    load_norm(s1, 8, sc[1], sh[1], threadIdx.x, 256);
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox; i += (long long)gridDim.x * blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            v[c] = act(__ldg(s0.x + c * nvox + i), sc[0][c], sh[0][c]) + act(__ldg(s1.x + c * nvox + i), sc[1][c], sh[1][c]);
+        out[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+        out[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------
+struct Dims { int D, H, W; long long n() const { return (long long)D * H * W; } };
+
+template <int CT, int STRIDE, bool IDENT>
+static int launch_conv(const ConvArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)a.Cin * 27 * CT * sizeof(float);
+    MVSN_CUDA_CHECK(cudaFuncSetAttribute(conv3d_k3_kernel<CT, STRIDE, IDENT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long nstrips = (long long)a.Dout * a.Hout * ((a.Wout + 3) / 4);
+    dim3 grid(cdiv(nstrips, 128), a.Cout / CT);
+    conv3d_k3_kernel<CT, STRIDE, IDENT><<<grid, 128, smem, st>>>(a);
+    MVSN_CUDA_CHECK(cudaGetLastError());
+    return MVSN_OK;
+}
+
+template <int CT>
+static int launch_deconv(const ConvArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)a.Cin * 27 * CT * sizeof(float);
+    MVSN_CUDA_CHECK(cudaFuncSetAttribute(deconv3d_k3s2_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long nstrips = (long long)a.Dout * a.Hout * ((a.Wout + 3) / 4);
+    dim3 grid(cdiv(nstrips, 128), a.Cout / CT);
+    deconv3d_k3s2_kernel<CT><<<grid, 128, smem, st>>>(a);
+    MVSN_CUDA_CHECK(cudaGetLastError());
+    return MVSN_OK;
+}
+
+}  // namespace mvsn
+
+using namespace mvsn;
+
+// layer table: conv0..conv6 (Conv3d), conv7/9/11 (ConvTranspose3d)
+static const int kCin[10]  = {41, 8, 16, 16, 32, 32, 64, 64, 32, 16};
+static const int kCout[10] = {8, 16, 16, 32, 32, 64, 64, 32, 16, 8};
+static const int kLevelOut[10] = {0, 1, 1, 2, 2, 3, 3, 2, 1, 0};     // resolution level of each layer's output
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" {
+
+size_t mvsn_costreg_workspace_bytes(int D, int Hp, int Wp) {
+    size_t total = 4096;                                       // statistics block (10 layers x <=64 ch x 2 doubles)
+    total += 10 * 64 * 2 * sizeof(double);
+    for (int l = 0; l < 10; ++l) {
+        const int s = 1 << kLevelOut[l];
+        total += align_up((size_t)kCout[l] * (D / s) * (Hp / s) * (Wp / s) * sizeof(float), 256);
+    }
+    return total;
+}
+
+int mvsn_costreg_forward(const float* const* w, const float* cost, int D, int Hp, int Wp, float* volume_dhwc,
+                         void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    MVSN_REQUIRE(w && cost && volume_dhwc && workspace, MVSN_ENULL, "mvsn_costreg_forward: NULL argument");
+    MVSN_REQUIRE(D > 0 && Hp > 0 && Wp > 0 && D % 8 == 0 && Hp % 8 == 0 && Wp % 8 == 0, MVSN_EBADSHAPE,
+                 "mvsn_costreg_forward: D=%d Hp=%d Wp=%d must all be divisible by 8 (three stride-2 levels, models.py:730-766)",
+                 D, Hp, Wp);
+    MVSN_REQUIRE(workspace_bytes >= mvsn_costreg_workspace_bytes(D, Hp, Wp), MVSN_EWORKSPACE,
+                 "mvsn_costreg_forward: workspace too small");
+    MVSN_REQUIRE(aligned16(workspace) && aligned16(volume_dhwc) && aligned16(cost), MVSN_EALIGN,
+                 "mvsn_costreg_forward: buffers must be 16-byte aligned");
+    for (int i = 0; i < MVSN_N_COSTREG_TENSORS; ++i)
+        MVSN_REQUIRE(w[i] != nullptr, MVSN_ENULL, "mvsn_costreg_forward: weight %d is NULL", i);
+
+    // carve the workspace
+    char* p = static_cast<char*>(workspace);
+    double* stats = reinterpret_cast<double*>(p);
+    const size_t stats_bytes = 10 * 64 * 2 * sizeof(double);
+    p += align_up(stats_bytes, 4096);
+    float* raw[10];
+    Dims dims[10];
+    for (int l = 0; l < 10; ++l) {
+        const int s = 1 << kLevelOut[l];
+        dims[l] = {D / s, Hp / s, Wp / s};
+        raw[l] = reinterpret_cast<float*>(p);
+        p += align_up((size_t)kCout[l] * dims[l].n() * sizeof(float), 256);
+    }
+    MVSN_CUDA_CHECK(cudaMemsetAsync(stats, 0, stats_bytes, st));
+
+    auto src = [&](int l) {
+        ActSrc s;
+        s.x = raw[l]; s.stats = stats + (size_t)l * 128; s.gamma = w[3 * l + 1]; s.beta = w[3 * l + 2];
+        s.count = (double)dims[l].n();
+        return s;
+    };
+    const ActSrc none{nullptr, nullptr, nullptr, nullptr, 1.0};
+    auto args = [&](int l, ActSrc a0, ActSrc a1, Dims din) {
+        ConvArgs a;
+        a.in0 = a0; a.in1 = a1; a.Cin = kCin[l]; a.Din = din.D; a.Hin = din.H; a.Win = din.W;
+        a.w = w[3 * l]; a.Cout = kCout[l]; a.Dout = dims[l].D; a.Hout = dims[l].H; a.Wout = dims[l].W;
+        a.out = raw[l]; a.stats_out = stats + (size_t)l * 128;
+        return a;
+    };
+    int rc;
+    ActSrc cost_src{cost, nullptr, nullptr, nullptr, 1.0};
+    const Dims full{D, Hp, Wp};
+    if ((rc = launch_conv<8, 1, true>(args(0, cost_src, none, full), st))) return rc;          // conv0 41->8
+    if ((rc = launch_conv<16, 2, false>(args(1, src(0), none, dims[0]), st))) return rc;       // conv1 8->16 s2
+    if ((rc = launch_conv<16, 1, false>(args(2, src(1), none, dims[1]), st))) return rc;       // conv2 16->16
+    if ((rc = launch_conv<16, 2, false>(args(3, src(2), none, dims[2]), st))) return rc;       // conv3 16->32 s2
+    if ((rc = launch_conv<16, 1, false>(args(4, src(3), none, dims[3]), st))) return rc;       // conv4 32->32
+    if ((rc = launch_conv<16, 2, false>(args(5, src(4), none, dims[4]), st))) return rc;       // conv5 32->64 s2
+    if ((rc = launch_conv<16, 1, false>(args(6, src(5), none, dims[5]), st))) return rc;       // conv6 64->64
+    if ((rc = launch_deconv<16>(args(7, src(6), none, dims[6]), st))) return rc;               // conv7  64->32
+    if ((rc = launch_deconv<16>(args(8, src(4), src(7), dims[7]), st))) return rc;             // conv9  (conv4 + .) 32->16
+    if ((rc = launch_deconv<8>(args(9, src(2), src(8), dims[8]), st))) return rc;              // conv11 (conv2 + .) 16->8
+    const long long nvox = full.n();
+    finalize_volume_kernel<<<cdiv(nvox, 256) < sm_count() * 8 ? cdiv(nvox, 256) : sm_count() * 8, 256, 0, st>>>(
+        src(0), src(9), nvox, reinterpret_cast<float4*>(volume_dhwc));
+    MVSN_CUDA_CHECK(cudaGetLastError());
+    return MVSN_OK;
+}
+
+}  // extern "C"

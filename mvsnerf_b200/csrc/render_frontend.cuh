@@ -1,0 +1,158 @@
+// Per-sample front end of the fused render kernel: everything the reference does between
+// "a ray" and "the 86-channel MLP input" (renderer.py:138-165 and callees), as device functions
+// shared by the fp32 and the tcgen05 render kernels.
+#pragma once
+#include "common.cuh"
+
+namespace mvsn {
+
+struct SceneDev {
+    const float* vol;      // [D,Hp,Wp,8]
+    const float4* imgs;    // [V,H,W] texels (r,g,b,0)
+    int D, Hp, Wp;
+    int V, H, W;
+    const float* w2cs;     // [V,4,4] device
+    const float* intrinsics;  // [V,3,3] device
+    int white_bkgd;
+};
+
+struct Cams {              // staged in shared memory by every render kernel
+    float w2c[3][12];
+    float K[3][9];
+};
+
+__device__ __forceinline__ void load_cams(const SceneDev& sc, Cams* cams, int tid) {
+    if (tid < 36) cams->w2c[tid / 12][tid % 12] = __ldg(sc.w2cs + (tid / 12) * 16 + tid % 12);
+    else if (tid < 63) { const int i = tid - 36; cams->K[i / 9][i % 9] = __ldg(sc.intrinsics + i); }
+}
+
+struct RayGenDev {
+    float near, far_minus_near;      // z normalisation of the reference camera (utils.py:128-131)
+    float inv_near, inv_far_minus_inv_near;
+    float pad, wf, hf;               // utils.py:138-143
+    int lindisp;
+};
+
+struct RenderIO {
+    // signature-compatible inputs (FAST == false)
+    const float* pts; const float* ndc; const float* z; const float* dirs;
+    // fused-caller inputs (FAST == true)
+    const float* rays; const float* t_steps;
+    RayGenDev rg;
+    int N, S;
+    float* rgb; float* depth; float* weights; float* alpha; float* input_feat;
+};
+
+int launch_render_fp32(const SceneDev& sc, const RenderIO& io, bool fast, const float* wts, cudaStream_t stream);
+
+// cam = R p + t ; pix = K cam ; (u, v) = pix.xy / pix.z / (W-1, H-1)     utils.py:120-127
+__device__ __forceinline__ void project_view(const float* __restrict__ w2c, const float* __restrict__ K,
+                                             float px, float py, float pz, float wm1, float hm1,
+                                             float& u, float& v, float& zc) {
+    float cx = fmaf(pz, w2c[2], fmaf(py, w2c[1], px * w2c[0])) + w2c[3];
+    float cy = fmaf(pz, w2c[6], fmaf(py, w2c[5], px * w2c[4])) + w2c[7];
+    float cz = fmaf(pz, w2c[10], fmaf(py, w2c[9], px * w2c[8])) + w2c[11];
+    float qx = fmaf(cz, K[2], fmaf(cy, K[1], cx * K[0]));
+    float qy = fmaf(cz, K[5], fmaf(cy, K[4], cx * K[3]));
+    float qz = fmaf(cz, K[8], fmaf(cy, K[7], cx * K[6]));
+    u = __fdiv_rn(__fdiv_rn(qx, qz), wm1);
+    v = __fdiv_rn(__fdiv_rn(qy, qz), hm1);
+    zc = qz;
+}
+
+// utils.get_ndc_coordinate for the reference camera (utils.py:112-146)
+__device__ __forceinline__ void ndc_of_point(const SceneDev& sc, const Cams& cams, const RayGenDev& rg,
+                                             float px, float py, float pz,
+                                             float& nx, float& ny, float& nz) {
+    float u, v, zc;
+    project_view(cams.w2c[0], cams.K[0], px, py, pz, (float)(sc.W - 1), (float)(sc.H - 1), u, v, zc);
+    if (!rg.lindisp) nz = __fdiv_rn(zc - rg.near, rg.far_minus_near);
+    else             nz = __fdiv_rn(__fdiv_rn(1.0f, zc) - rg.inv_near, rg.inv_far_minus_inv_near);
+    if (rg.pad > 0.f) {
+        float dh = rg.hf + rg.pad * 2.f, dw = rg.wf + rg.pad * 2.f;
+        v = __fadd_rn(__fdiv_rn(__fmul_rn(v, rg.hf), dh), __fdiv_rn(rg.pad, dh));
+        u = __fadd_rn(__fdiv_rn(__fmul_rn(u, rg.wf), dw), __fdiv_rn(rg.pad, dw));
+    }
+    nx = u; ny = v;
+}
+
+// utils.index_point_feature (utils.py:357-383): trilinear, zeros padding, align_corners=True
+__device__ __forceinline__ void sample_volume(const SceneDev& sc, float nx, float ny, float nz, float* out8) {
+    const int W = sc.Wp, H = sc.Hp, D = sc.D;
+    float ix = ((nx * 2.f - 1.f + 1.f) * 0.5f) * (float)(W - 1);
+    float iy = ((ny * 2.f - 1.f + 1.f) * 0.5f) * (float)(H - 1);
+    float iz = ((nz * 2.f - 1.f + 1.f) * 0.5f) * (float)(D - 1);
+    float x0f = floorf(ix), y0f = floorf(iy), z0f = floorf(iz);
+    float wx1 = ix - x0f, wy1 = iy - y0f, wz1 = iz - z0f;
+    float wx0 = (x0f + 1.f) - ix, wy0 = (y0f + 1.f) - iy, wz0 = (z0f + 1.f) - iz;
+    // clamp before the int conversion so absurd coordinates cannot overflow
+    int x0 = (int)fminf(fmaxf(x0f, -2.f), (float)W);
+    int y0 = (int)fminf(fmaxf(y0f, -2.f), (float)H);
+    int z0 = (int)fminf(fmaxf(z0f, -2.f), (float)D);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) out8[c] = 0.f;
+#pragma unroll
+    for (int dz = 0; dz < 2; ++dz) {
+        int z = z0 + dz;
+        float wz = dz ? wz1 : wz0;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            int y = y0 + dy;
+            float wy = dy ? wy1 : wy0;
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                int x = x0 + dx;
+                float wx = dx ? wx1 : wx0;
+                if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H && (unsigned)z < (unsigned)D) {
+                    const float4* p = reinterpret_cast<const float4*>(
+                        sc.vol + (((size_t)z * H + y) * W + x) * 8);
+                    float4 a = __ldg(p), b = __ldg(p + 1);
+                    float wgt = wx * wy * wz;
+                    out8[0] = fmaf(a.x, wgt, out8[0]); out8[1] = fmaf(a.y, wgt, out8[1]);
+                    out8[2] = fmaf(a.z, wgt, out8[2]); out8[3] = fmaf(a.w, wgt, out8[3]);
+                    out8[4] = fmaf(b.x, wgt, out8[4]); out8[5] = fmaf(b.y, wgt, out8[5]);
+                    out8[6] = fmaf(b.z, wgt, out8[6]); out8[7] = fmaf(b.w, wgt, out8[7]);
+                }
+            }
+        }
+    }
+}
+
+// utils.build_color_volume (utils.py:300-332): bilinear, BORDER padding, strict in-bounds mask.
+// out4 = (r, g, b, mask)
+__device__ __forceinline__ void sample_color(const SceneDev& sc, const Cams& cams, int v, float px, float py, float pz, float* out4) {
+    const int W = sc.W, H = sc.H;
+    float u, vv, zc;
+    project_view(cams.w2c[v], cams.K[v], px, py, pz, (float)(W - 1), (float)(H - 1), u, vv, zc);
+    float gx = u * 2.f - 1.f, gy = vv * 2.f - 1.f;
+    float ix = ((gx + 1.f) * 0.5f) * (float)(W - 1);
+    float iy = ((gy + 1.f) * 0.5f) * (float)(H - 1);
+    ix = fminf(fmaxf(ix, 0.f), (float)(W - 1));    // border: clip the source index
+    iy = fminf(fmaxf(iy, 0.f), (float)(H - 1));
+    float x0f = floorf(ix), y0f = floorf(iy);
+    float wx1 = ix - x0f, wy1 = iy - y0f, wx0 = (x0f + 1.f) - ix, wy0 = (y0f + 1.f) - iy;
+    int x0 = (int)x0f, y0 = (int)y0f;
+    if (!(ix == ix)) { x0 = 0; }   // NaN coordinate: keep addresses legal; weights propagate NaN
+    if (!(iy == iy)) { y0 = 0; }
+    int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);   // the clipped tap always has weight 0
+    const float4* img = sc.imgs + (size_t)v * H * W;
+    float4 nw = __ldg(img + (size_t)y0 * W + x0), ne = __ldg(img + (size_t)y0 * W + x1);
+    float4 sw = __ldg(img + (size_t)y1 * W + x0), se = __ldg(img + (size_t)y1 * W + x1);
+    float a = wx0 * wy0, b = wx1 * wy0, c = wx0 * wy1, d = wx1 * wy1;
+    out4[0] = fmaf(se.x, d, fmaf(sw.x, c, fmaf(ne.x, b, nw.x * a)));
+    out4[1] = fmaf(se.y, d, fmaf(sw.y, c, fmaf(ne.y, b, nw.y * a)));
+    out4[2] = fmaf(se.z, d, fmaf(sw.z, c, fmaf(ne.z, b, nw.z * a)));
+    out4[3] = (gx > -1.f && gx < 1.f && gy > -1.f && gy < 1.f) ? 1.f : 0.f;
+}
+
+// gen_dir_feature (renderer.py:111-122,142-147): unit direction in the reference camera frame
+__device__ __forceinline__ void view_dir(const Cams& cams, float dx, float dy, float dz, float* out3) {
+    float n = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    dx = __fdiv_rn(dx, n); dy = __fdiv_rn(dy, n); dz = __fdiv_rn(dz, n);
+    const float* R = cams.w2c[0];
+    out3[0] = fmaf(dz, R[2], fmaf(dy, R[1], dx * R[0]));
+    out3[1] = fmaf(dz, R[6], fmaf(dy, R[5], dx * R[4]));
+    out3[2] = fmaf(dz, R[10], fmaf(dy, R[9], dx * R[8]));
+}
+
+}  // namespace mvsn
