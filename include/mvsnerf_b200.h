@@ -154,6 +154,13 @@ int mvsn_costreg_forward(const float* const* w_host_array_of_device_ptrs, const 
                          int D, int Hp, int Wp, float* volume_dhwc,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Diagnostic: one 128 x N x K fp16 GEMM (fp32 accumulate) through the same tcgen05 building blocks
+ * the fused render kernel uses.  A [128,K], B [N,K] fp16 row-major; Bc [N,16] optional extra K-step
+ * (D += A[:,16:32] * Bc^T, the "bias" step); D [128,N] fp32.  Used by tests only.
+ * ------------------------------------------------------------------------------------- */
+int mvsn_selftest_umma(const void* A, const void* B, const void* Bc, int N, int K, float* D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

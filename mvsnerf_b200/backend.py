@@ -460,6 +460,34 @@ def render_rays(rays, volume_feature, imgs, pose_ref, network_fn, near_far, pad,
     return rgb, depth
 
 
+class HostFrameRenderer:
+    """Host-buffer entry: rays arrive in (pinned) host memory, pixels are returned in host memory.
+
+    This is the call the notebooks' frame loop makes in effect (`rgb.cpu()` / `depth_pred.cpu()` per
+    chunk, renderer_video.ipynb DTU cell) collapsed to one H2D copy, one launch, one D2H copy."""
+
+    def __init__(self, n_rays, device):
+        self.n, self.device = int(n_rays), torch.device(device)
+        self.rays_dev = torch.empty(self.n, 8, dtype=torch.float32, device=self.device)
+        self.rgb_dev = torch.empty(self.n, 3, dtype=torch.float32, device=self.device)
+        self.depth_dev = torch.empty(self.n, dtype=torch.float32, device=self.device)
+        self.rgb_host = torch.empty(self.n, 3, dtype=torch.float32).pin_memory()
+        self.depth_host = torch.empty(self.n, dtype=torch.float32).pin_memory()
+        self.h2d_bytes = self.n * 8 * 4
+        self.d2h_bytes = self.n * 4 * 4
+
+    def render(self, rays_host, volume_feature, imgs, pose_ref, network_fn, near_far, pad, **kw):
+        if rays_host.is_cuda or tuple(rays_host.shape) != (self.n, 8):
+            raise RuntimeError(f"HostFrameRenderer: expected a host tensor [{self.n}, 8]")
+        self.rays_dev.copy_(rays_host, non_blocking=True)
+        render_rays(self.rays_dev, volume_feature, imgs, pose_ref, network_fn, near_far, pad,
+                    out=(self.rgb_dev, self.depth_dev), **kw)
+        self.rgb_host.copy_(self.rgb_dev, non_blocking=True)
+        self.depth_host.copy_(self.depth_dev, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.rgb_host, self.depth_host
+
+
 # --------------------------------------------------------------------------------------------
 # factory (models.py:569-654)
 # --------------------------------------------------------------------------------------------
