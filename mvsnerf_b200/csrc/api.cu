@@ -122,6 +122,8 @@ static int dispatch_render(const mvsn_render_scene* scene, const SceneDev& sc, c
     switch (scene->mlp_mode) {
         case MVSN_MLP_FP32:
             return launch_render_fp32(sc, io, fast, static_cast<const float*>(scene->mlp_packed), stream);
+        case MVSN_MLP_TC_HALF:
+            return launch_render_tc(sc, io, fast, scene->mlp_packed, stream);
         default:
             set_error("mlp_mode %d is not available in this build", scene->mlp_mode);
             return MVSN_EUNSUPPORTED;
@@ -140,6 +142,7 @@ int mvsn_abi_version(void) { return 1; }
 size_t mvsn_mlp_packed_bytes(int mode) {
     switch (mode) {
         case MVSN_MLP_FP32: return (size_t)w32::TOTAL * sizeof(float);
+        case MVSN_MLP_TC_HALF: return mlp_tc_packed_bytes();
         default: return 0;
     }
 }
@@ -155,6 +158,7 @@ int mvsn_mlp_pack(const float* const* w, int mode, void* packed, size_t packed_b
         MVSN_REQUIRE(w[i] != nullptr, MVSN_ENULL, "mvsn_mlp_pack: tensor %d is NULL", i);
         p.p[i] = w[i];
     }
+    if (mode == MVSN_MLP_TC_HALF) return pack_mlp_tc(w, packed, (cudaStream_t)stream);
     pack_mlp_fp32_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(p, static_cast<float*>(packed));
     MVSN_CUDA_CHECK(cudaGetLastError());
     return MVSN_OK;

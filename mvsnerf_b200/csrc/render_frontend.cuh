@@ -44,6 +44,9 @@ struct RenderIO {
 };
 
 int launch_render_fp32(const SceneDev& sc, const RenderIO& io, bool fast, const float* wts, cudaStream_t stream);
+int launch_render_tc(const SceneDev& sc, const RenderIO& io, bool fast, const void* wimg, cudaStream_t stream);
+size_t mlp_tc_packed_bytes();
+int pack_mlp_tc(const float* const* w, void* packed, cudaStream_t stream);
 
 // cam = R p + t ; pix = K cam ; (u, v) = pix.xy / pix.z / (W-1, H-1)     utils.py:120-127
 __device__ __forceinline__ void project_view(const float* __restrict__ w2c, const float* __restrict__ K,
