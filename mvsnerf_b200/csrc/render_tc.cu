@@ -1,13 +1,13 @@
 // K-C, tensor-core mode (MVSN_MLP_TC_HALF): the fused per-ray render kernel with the per-sample MLP
 // on the 5th-generation tensor cores (tcgen05.mma, fp16 operands, fp32 accumulators in TMEM).
 //
-// One persistent CTA per SM, 320 threads in four roles:
-//   warps 0-3   slot 0 group : front end (ray march, NDC, trilinear + colour gather, positional
-//   warps 4-7   slot 1 group   encoding -> fp16 operand tiles in shared memory), per-layer
+// One persistent CTA per SM, 576 threads in four roles:
+//   warps 0-7   slot 0 group : front end (ray march, NDC, trilinear + colour gather, positional
+//   warps 8-15  slot 1 group   encoding -> fp16 operand tiles in shared memory), per-layer
 //                              epilogues (TMEM -> registers -> modulation/ReLU -> fp16 -> smem) and
-//                              alpha compositing; one thread per sample row
-//   warp 8      MMA issuer   : one thread issues every tcgen05.mma of both slots and the commits
-//   warp 9      weight loader: one thread streams the pre-swizzled weight image L2 -> smem ring with
+//                              alpha compositing; two threads per sample row (column halves)
+//   warp 16     MMA issuer   : one thread issues every tcgen05.mma of both slots and the commits
+//   warp 17     weight loader: one thread streams the pre-swizzled weight image L2 -> smem ring with
 //                              1-D bulk async copies (cp.async.bulk + mbarrier complete_tx)
 // Two 128-sample tiles ("slots") are in flight per CTA and run the nine GEMM phases in lock step,
 // so each streamed weight chunk serves both tiles and one slot's epilogue overlaps the other
@@ -42,14 +42,14 @@ constexpr int STAGE_BYTES = 24576;
 constexpr int NSTAGE = 4;
 }  // namespace tcw
 
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 576;                           // 16 slot warps + MMA issuer + weight loader
 constexpr int SLOT_BYTES = 65536;                           // PE 16K | H0 16K | H1 16K | MISC 16K
 constexpr int OFF_PE = 0, OFF_H0 = 16384, OFF_H1 = 32768, OFF_MISC = 49152;
 constexpr int RING_OFFSET = 2 * SLOT_BYTES;
 constexpr int TC_SMEM_BYTES = RING_OFFSET + tcw::NSTAGE * tcw::STAGE_BYTES + 1024;
 
 struct TcShared {
-    uint64_t in_ready[2];       // slot group (128 arrivals) -> MMA issuer: operand tile written
+    uint64_t in_ready[2][2];    // slot group part (128 arrivals each) -> MMA issuer: operand columns written
     uint64_t acc_ready[2];      // tcgen05.commit -> slot group: accumulator complete
     uint64_t w_full[tcw::NSTAGE];
     uint64_t w_empty[tcw::NSTAGE];
@@ -66,31 +66,48 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
-
-// ---- epilogue: relu(acc * mod) -> fp16 -> H tile (K columns c0 .. c0+31 of row `row`) -----------
-template <bool MODULATE, bool RELU>
-__device__ __forceinline__ void epilogue_cols32(uint32_t t_acc, uint32_t t_mod, int c0, uint8_t* slot, int row) {
-    uint32_t a[32], m[32];
-    tmem_ld32(t_acc + c0, a);
-    if (MODULATE) tmem_ld32(t_mod + c0, m);
-    tmem_ld_wait();
-    uint8_t* blk = slot + (c0 < 64 ? OFF_H0 : OFF_H1);
-    const int kc0 = (c0 & 63) >> 3;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {             // 4 chunks of 8 columns
-        uint32_t p[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float x0 = __uint_as_float(a[q * 8 + 2 * j]), x1 = __uint_as_float(a[q * 8 + 2 * j + 1]);
-            if (MODULATE) { x0 *= __uint_as_float(m[q * 8 + 2 * j]); x1 *= __uint_as_float(m[q * 8 + 2 * j + 1]); }
-            if (RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-            p[j] = pack_h2(x0, x1);
-        }
-        *reinterpret_cast<uint4*>(blk + sw128_offset(row, (kc0 + q) * 8)) = make_uint4(p[0], p[1], p[2], p[3]);
-    }
+// tcgen05.wait::ld that also names the destination registers, so no use can be scheduled above it
+__device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :: "memory");
 }
 
-struct TcIO { RenderIO io; };
+// 16 accumulator columns -> (x mod) -> relu -> fp16 -> two 16-byte chunks of an operand K-block
+template <bool MODULATE, bool RELU>
+__device__ __forceinline__ void emit16(const uint32_t (&a)[16], const uint32_t (&m)[16], uint8_t* blk, int row, int kc) {
+    uint32_t p[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float2 x = make_float2(__uint_as_float(a[2 * j]), __uint_as_float(a[2 * j + 1]));
+        if (MODULATE) x = __fmul2_rn(x, make_float2(__uint_as_float(m[2 * j]), __uint_as_float(m[2 * j + 1])));
+        __half2 h = __floats2half2_rn(x.x, x.y);
+        if (RELU) h = __hmax2(h, __float2half2_rn(0.f));
+        p[j] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(blk + sw128_offset(row, kc * 8)) = make_uint4(p[0], p[1], p[2], p[3]);
+    *reinterpret_cast<uint4*>(blk + sw128_offset(row, kc * 8 + 8)) = make_uint4(p[4], p[5], p[6], p[7]);
+}
+
+// epilogue over NCOL (multiple of 16) accumulator columns starting at t_acc / t_mod, written to
+// K-block `blk` starting at 16-byte chunk kc0; TMEM loads of chunk i+1 fly while chunk i is processed
+template <int NCOL, bool MODULATE, bool RELU>
+__device__ __forceinline__ void epilogue(uint32_t t_acc, uint32_t t_mod, uint8_t* blk, int row, int kc0) {
+    uint32_t a[2][16], m[2][16];
+    tmem_ld16(t_acc, a[0]);
+    if (MODULATE) tmem_ld16(t_mod, m[0]);
+#pragma unroll
+    for (int i = 0; i < NCOL / 16; ++i) {
+        tmem_wait16(a[i & 1]);
+        if (MODULATE) tmem_wait16(m[i & 1]);
+        if (i + 1 < NCOL / 16) {
+            tmem_ld16(t_acc + (i + 1) * 16, a[(i + 1) & 1]);
+            if (MODULATE) tmem_ld16(t_mod + (i + 1) * 16, m[(i + 1) & 1]);
+        }
+        emit16<MODULATE, RELU>(a[i & 1], m[i & 1], blk, row, kc0 + 2 * i);
+    }
+}
 
 template <bool FAST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -102,11 +119,14 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
 
     load_cams(sc, &sh.cams, tid);
     if (tid == 0) {
-        for (int s = 0; s < 2; ++s) { mbar_init(&sh.in_ready[s], 128); mbar_init(&sh.acc_ready[s], 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&sh.in_ready[s][0], 128); mbar_init(&sh.in_ready[s][1], 128);
+            mbar_init(&sh.acc_ready[s], 1);
+        }
         for (int i = 0; i < tcw::NSTAGE; ++i) { mbar_init(&sh.w_full[i], 1); mbar_init(&sh.w_empty[i], 1); }
         fence_barrier_init();
     }
-    if (warp == 8) { tmem_alloc(&sh.tmem_base, 512); tmem_relinquish(); }
+    if (warp == 16) { tmem_alloc(&sh.tmem_base, 512); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -122,16 +142,20 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
     const int npass = my_pairs * nchunks;                    // one tile per active slot per pass
     auto group_of = [&](int pass, int s) { return ((pass / nchunks) * (int)gridDim.x + (int)blockIdx.x) * 2 + s; };
 
-    if (warp < 8) {
+    if (warp < 16) {
         // =========================== slot group: front end + epilogues + compositing ===============
-        const int s = warp >> 2, row = tid & 127, wq = warp & 3;
+        // part 0 (warps 0-3 of the slot): accumulator columns 0..63, volume fetch, sin half of the
+        // encoding, compositing.  part 1 (warps 4-7): columns 64..127, colour fetch, cos half.
+        const int s = warp >> 3, part = (warp >> 2) & 1, wq = warp & 3, row = wq * 32 + lane;
         uint8_t* slot = smem + s * SLOT_BYTES;
         const uint32_t t_acc = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(s * 256);
         const uint32_t t_mod = t_acc + 128;
-        uint32_t par_acc = 0;
+        uint32_t par_acc = 0, par_op8 = 0;
+        bool pending_op8 = false;                            // part 1 skips the op-8 wait; it is made up before the next arrive
         const float br0 = __ldg(reinterpret_cast<const float*>(wimg + tcw::TAIL_OFFSET));
         const float br1 = __ldg(reinterpret_cast<const float*>(wimg + tcw::TAIL_OFFSET) + 1);
         const float br2 = __ldg(reinterpret_cast<const float*>(wimg + tcw::TAIL_OFFSET) + 2);
+        uint8_t* hblk = slot + (part ? OFF_H1 : OFF_H0);
 
         for (int pass = 0; pass < npass; ++pass) {
             const int g = group_of(pass, s), chunk = pass % nchunks;
@@ -141,12 +165,10 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
             if (S <= 128) { r_in = row / S; s_idx = row - r_in * S; } else { r_in = 0; s_idx = chunk * 128 + row; }
             const int ray = g * R + r_in;
             const bool valid = ray < N;
-            float pe[3] = {0.f, 0.f, 0.f}, feat[20], dir[3] = {0.f, 0.f, 0.f}, zv = 0.f;
-#pragma unroll
-            for (int i = 0; i < 20; ++i) feat[i] = 0.f;
             const size_t si = (size_t)ray * S + s_idx;
+            float nx = 0.f, ny = 0.f, nz = 0.f, zv = 0.f;
+            float px = 0.f, py = 0.f, pz = 0.f, dx = 0.f, dy = 0.f, dz = 1.f;
             if (valid) {
-                float px, py, pz, dx, dy, dz;
                 if (FAST) {
                     const float4* rp = reinterpret_cast<const float4*>(io.rays + (size_t)ray * 8);
                     float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
@@ -158,94 +180,127 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                     px = __fadd_rn(r0.x, __fmul_rn(dx, zv));
                     py = __fadd_rn(r0.y, __fmul_rn(dy, zv));
                     pz = __fadd_rn(r0.z, __fmul_rn(dz, zv));
-                    ndc_of_point(sc, sh.cams, io.rg, px, py, pz, pe[0], pe[1], pe[2]);
+                    ndc_of_point(sc, sh.cams, io.rg, px, py, pz, nx, ny, nz);
                 } else {
                     px = __ldg(io.pts + si * 3); py = __ldg(io.pts + si * 3 + 1); pz = __ldg(io.pts + si * 3 + 2);
-                    pe[0] = __ldg(io.ndc + si * 3); pe[1] = __ldg(io.ndc + si * 3 + 1); pe[2] = __ldg(io.ndc + si * 3 + 2);
+                    nx = __ldg(io.ndc + si * 3); ny = __ldg(io.ndc + si * 3 + 1); nz = __ldg(io.ndc + si * 3 + 2);
                     zv = __ldg(io.z + si);
                     dx = __ldg(io.dirs + (size_t)ray * 3); dy = __ldg(io.dirs + (size_t)ray * 3 + 1);
                     dz = __ldg(io.dirs + (size_t)ray * 3 + 2);
                 }
-                view_dir(sh.cams, dx, dy, dz, dir);
-                sample_volume(sc, pe[0], pe[1], pe[2], feat);
-#pragma unroll
-                for (int v = 0; v < 3; ++v) sample_color(sc, sh.cams, v, px, py, pz, feat + 8 + 4 * v);
-                if (io.input_feat) {
-                    float4* o = reinterpret_cast<float4*>(io.input_feat + si * 20);
-#pragma unroll
-                    for (int i = 0; i < 5; ++i)
-                        o[i] = make_float4(feat[4 * i], feat[4 * i + 1], feat[4 * i + 2], feat[4 * i + 3]);
-                }
             }
-            {   // positional encoding -> PE tile: [x(3), sin(2^k x) k-major, cos(2^k x) k-major, 1]
-                float v[64];
-                v[0] = pe[0]; v[1] = pe[1]; v[2] = pe[2];
+            const float nd[3] = {nx, ny, nz};
+            if (part == 0) {
+                // volume features (8) -> MISC cols 0..7 ; PE cols 0..31 = [x y z | sin(2^k x) for 29 of 30]
+                float feat[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) feat[i] = 0.f;
+                if (valid) {
+                    sample_volume(sc, nx, ny, nz, feat);
+                    if (io.input_feat) {
+                        float4* o = reinterpret_cast<float4*>(io.input_feat + si * 20);
+                        o[0] = make_float4(feat[0], feat[1], feat[2], feat[3]);
+                        o[1] = make_float4(feat[4], feat[5], feat[6], feat[7]);
+                    }
+                }
+                *reinterpret_cast<uint4*>(slot + OFF_MISC + sw128_offset(row, 0)) =
+                    make_uint4(pack_h2(feat[0], feat[1]), pack_h2(feat[2], feat[3]), pack_h2(feat[4], feat[5]), pack_h2(feat[6], feat[7]));
+                float v[32];
+                v[0] = nx; v[1] = ny; v[2] = nz;
                 float f = 1.f;
 #pragma unroll
                 for (int k = 0; k < 10; ++k) {
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) sincosf(pe[j] * f, &v[3 + 3 * k + j], &v[33 + 3 * k + j]);
+                    for (int j = 0; j < 3; ++j)
+                        if (3 + 3 * k + j < 32) v[3 + 3 * k + j] = __sinf(nd[j] * f);
                     f *= 2.f;
                 }
-                v[63] = 1.f;
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
+                for (int c = 0; c < 4; ++c)
                     *reinterpret_cast<uint4*>(slot + OFF_PE + sw128_offset(row, c * 8)) =
                         make_uint4(pack_h2(v[c * 8], v[c * 8 + 1]), pack_h2(v[c * 8 + 2], v[c * 8 + 3]),
                                    pack_h2(v[c * 8 + 4], v[c * 8 + 5]), pack_h2(v[c * 8 + 6], v[c * 8 + 7]));
-            }
-            {   // MISC tile: [feat 0..19, 1, 0 x11 | dir 0..2, 1, 0 x12 | unused 16]
+            } else {
+                // colour features (12) + view direction -> MISC cols 8..47 ; PE cols 32..63 = [sin(512 z) | cos | 1]
+                float feat[12], dir[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int i = 0; i < 12; ++i) feat[i] = 0.f;
+                if (valid) {
+                    view_dir(sh.cams, dx, dy, dz, dir);
+#pragma unroll
+                    for (int v = 0; v < 3; ++v) sample_color(sc, sh.cams, v, px, py, pz, feat + 4 * v);
+                    if (io.input_feat) {
+                        float4* o = reinterpret_cast<float4*>(io.input_feat + si * 20) + 2;
+                        o[0] = make_float4(feat[0], feat[1], feat[2], feat[3]);
+                        o[1] = make_float4(feat[4], feat[5], feat[6], feat[7]);
+                        o[2] = make_float4(feat[8], feat[9], feat[10], feat[11]);
+                    }
+                }
                 uint8_t* m = slot + OFF_MISC;
-                *reinterpret_cast<uint4*>(m + sw128_offset(row, 0)) =
-                    make_uint4(pack_h2(feat[0], feat[1]), pack_h2(feat[2], feat[3]), pack_h2(feat[4], feat[5]), pack_h2(feat[6], feat[7]));
                 *reinterpret_cast<uint4*>(m + sw128_offset(row, 8)) =
-                    make_uint4(pack_h2(feat[8], feat[9]), pack_h2(feat[10], feat[11]), pack_h2(feat[12], feat[13]), pack_h2(feat[14], feat[15]));
+                    make_uint4(pack_h2(feat[0], feat[1]), pack_h2(feat[2], feat[3]), pack_h2(feat[4], feat[5]), pack_h2(feat[6], feat[7]));
                 *reinterpret_cast<uint4*>(m + sw128_offset(row, 16)) =
-                    make_uint4(pack_h2(feat[16], feat[17]), pack_h2(feat[18], feat[19]), pack_h2(1.f, 0.f), 0u);
+                    make_uint4(pack_h2(feat[8], feat[9]), pack_h2(feat[10], feat[11]), pack_h2(1.f, 0.f), 0u);
                 *reinterpret_cast<uint4*>(m + sw128_offset(row, 24)) = make_uint4(0u, 0u, 0u, 0u);
                 *reinterpret_cast<uint4*>(m + sw128_offset(row, 32)) =
                     make_uint4(pack_h2(dir[0], dir[1]), pack_h2(dir[2], 1.f), 0u, 0u);
                 *reinterpret_cast<uint4*>(m + sw128_offset(row, 40)) = make_uint4(0u, 0u, 0u, 0u);
+                float v[32];
+                v[0] = __sinf(nz * 512.f);
+                float f = 1.f;
+#pragma unroll
+                for (int k = 0; k < 10; ++k) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) v[1 + 3 * k + j] = __cosf(nd[j] * f);
+                    f *= 2.f;
+                }
+                v[31] = 1.f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<uint4*>(slot + OFF_PE + sw128_offset(row, 32 + c * 8)) =
+                        make_uint4(pack_h2(v[c * 8], v[c * 8 + 1]), pack_h2(v[c * 8 + 2], v[c * 8 + 3]),
+                                   pack_h2(v[c * 8 + 4], v[c * 8 + 5]), pack_h2(v[c * 8 + 6], v[c * 8 + 7]));
             }
             fence_proxy_async();
-            mbar_arrive(&sh.in_ready[s]);
+            if (pending_op8) { mbar_wait(&sh.acc_ready[s], par_op8); pending_op8 = false; }   // previous tile's op 8 retired
+            mbar_arrive(&sh.in_ready[s][part]);
 
             // -------------------------- trunk: ops 0..5 -> h ------------------------------------------
 #pragma unroll 1
             for (int op = 0; op < 6; ++op) {
                 mbar_wait(&sh.acc_ready[s], par_acc); par_acc ^= 1;
                 tc_fence_after();
-#pragma unroll
-                for (int c0 = 0; c0 < 128; c0 += 32) epilogue_cols32<true, true>(t_acc, t_mod, c0, slot, row);
+                epilogue<64, true, true>(t_acc + part * 64, t_mod + part * 64, hblk, row, 0);
                 tc_fence_before();
                 fence_proxy_async();
-                mbar_arrive(&sh.in_ready[s]);
+                mbar_arrive(&sh.in_ready[s][part]);
             }
             // -------------------------- op 6: feature (128) + sigma (col 128) ---------------------------
-            float sigma;
+            float sigma = 0.f;
             {
                 mbar_wait(&sh.acc_ready[s], par_acc); par_acc ^= 1;
                 tc_fence_after();
-#pragma unroll
-                for (int c0 = 0; c0 < 128; c0 += 32) epilogue_cols32<false, false>(t_acc, t_mod, c0, slot, row);
-                uint32_t r16[16];
-                tmem_ld16(t_acc + 128, r16);
-                tmem_ld_wait();
-                sigma = fmaxf(__uint_as_float(r16[0]), 0.f);
+                epilogue<64, false, false>(t_acc + part * 64, t_mod, hblk, row, 0);
+                if (part == 0) {
+                    uint32_t r16[16];
+                    tmem_ld16(t_acc + 128, r16);
+                    tmem_wait16(r16);
+                    sigma = fmaxf(__uint_as_float(r16[0]), 0.f);
+                }
                 tc_fence_before();
                 fence_proxy_async();
-                mbar_arrive(&sh.in_ready[s]);
+                mbar_arrive(&sh.in_ready[s][part]);
             }
-            // -------------------------- op 7: views layer (64) ---------------------------------------------
+            // -------------------------- op 7: views layer (64 = 2 x 32) ------------------------------------
             {
                 mbar_wait(&sh.acc_ready[s], par_acc); par_acc ^= 1;
                 tc_fence_after();
-                epilogue_cols32<false, true>(t_acc, t_mod, 0, slot, row);
-                epilogue_cols32<false, true>(t_acc, t_mod, 32, slot, row);
+                epilogue<32, false, true>(t_acc + part * 32, t_mod, slot + OFF_H0, row, part * 4);
                 tc_fence_before();
                 fence_proxy_async();
-                mbar_arrive(&sh.in_ready[s]);
+                mbar_arrive(&sh.in_ready[s][part]);
             }
+            if (part == 1) { par_op8 = par_acc; par_acc ^= 1; pending_op8 = true; continue; }   // op 8 + compositing: part 0
             // -------------------------- op 8: rgb ----------------------------------------------------------
             float cr, cg, cb;
             {
@@ -253,15 +308,15 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                 tc_fence_after();
                 uint32_t r16[16];
                 tmem_ld16(t_acc, r16);
-                tmem_ld_wait();
+                tmem_wait16(r16);
                 tc_fence_before();
-                cr = __fdiv_rn(1.f, 1.f + expf(-(__uint_as_float(r16[0]) + br0)));
-                cg = __fdiv_rn(1.f, 1.f + expf(-(__uint_as_float(r16[1]) + br1)));
-                cb = __fdiv_rn(1.f, 1.f + expf(-(__uint_as_float(r16[2]) + br2)));
+                cr = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(r16[0]) + br0)));
+                cg = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(r16[1]) + br1)));
+                cb = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(r16[2]) + br2)));
             }
             // -------------------------- compositing (renderer.py:18-26,65-92) ----------------------------------
             {
-                const float alpha = 1.f - expf(-sigma);
+                const float alpha = 1.f - __expf(-sigma);
                 const float fac = (1.f - alpha) + 1e-10f;
                 const int seg = S < 32 ? S : 32;                  // scan segment inside a warp
                 const int ls = lane & (seg - 1);
@@ -273,14 +328,13 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                 }
                 float T = __shfl_up_sync(0xffffffffu, incl, 1);
                 if (ls == 0) T = 1.f;
-                if (S > 32) {                                     // rays span S/32 (<= 4) warps of this group
+                const int wpr = S >= 128 ? 4 : (S > 32 ? S / 32 : 1);   // warps per ray inside a tile
+                if (S > 32) {
                     if (lane == 31) sh.scan[s][wq][0] = incl;
                     named_bar_sync(1 + s, 128);
-                    const int wpr = S >= 128 ? 4 : S / 32;        // warps per ray inside a tile
                     const int w0 = wq - (wq % wpr);
                     for (int w = w0; w < wq; ++w) T *= sh.scan[s][w][0];
                     if (nchunks > 1 && chunk > 0) T *= sh.carry[s][0];
-                    named_bar_sync(1 + s, 128);
                 }
                 const float wgt = alpha * T;
                 if (valid) {
@@ -302,7 +356,6 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                         sh.scan[s][wq][4] = v3; sh.scan[s][wq][5] = v4;
                     }
                     named_bar_sync(1 + s, 128);
-                    const int wpr = S >= 128 ? 4 : S / 32;
                     if (lane == 0 && (wq % wpr) == 0) {
                         for (int w = wq + 1; w < wq + wpr; ++w) {
                             v0 += sh.scan[s][w][1]; v1 += sh.scan[s][w][2]; v2 += sh.scan[s][w][3];
@@ -319,9 +372,9 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                             sh.carry[s][4] = v3; sh.carry[s][5] = v4;
                         }
                     }
-                    named_bar_sync(1 + s, 128);
+                    named_bar_sync(1 + s, 128);               // scratch + carry are stable before the next tile
                 }
-                const bool writer = S > 32 ? (lane == 0 && (wq % (S >= 128 ? 4 : S / 32)) == 0) : (ls == 0);
+                const bool writer = S > 32 ? (lane == 0 && (wq % wpr) == 0) : (ls == 0);
                 if (writer && valid && chunk == nchunks - 1) {
                     if (sc.white_bkgd) { const float bg = 1.f - v4; v0 += bg; v1 += bg; v2 += bg; }
                     io.rgb[(size_t)ray * 3 + 0] = v0; io.rgb[(size_t)ray * 3 + 1] = v1; io.rgb[(size_t)ray * 3 + 2] = v2;
@@ -329,7 +382,7 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == 16) {
         // =========================== MMA issuer ========================================================
         if (lane == 0) {
             uint32_t par_in[2] = {0, 0};
@@ -337,6 +390,11 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
             const uint32_t ring = sbase + RING_OFFSET;
             constexpr uint32_t ID128 = idesc_f16(128, 128), ID144 = idesc_f16(128, 144),
                                ID64 = idesc_f16(128, 64), ID16 = idesc_f16(128, 16);
+            // descriptors: hi word constant per layout, lo word = (addr >> 4) | LBO field; a K-step adds 32 B = 2 units
+            constexpr uint32_t HI_SW = (uint32_t)(desc_sw128(0) >> 32), HI_NS = (uint32_t)(desc_nosw(0, 128, 256) >> 32);
+            constexpr uint32_t LO_SW = (uint32_t)desc_sw128(0), LO_NS = (uint32_t)desc_nosw(0, 128, 256);
+            auto dsw = [&](uint32_t addr) { return ((uint64_t)HI_SW << 32) | (uint64_t)(LO_SW | (addr >> 4)); };
+            auto dns = [&](uint32_t addr) { return ((uint64_t)HI_NS << 32) | (uint64_t)(LO_NS | (addr >> 4)); };
             uint32_t nchunk_base = 0;                         // global chunk counter at the start of the pass
             for (int pass = 0; pass < npass; ++pass) {
                 const bool act[2] = {group_of(pass, 0) < G, group_of(pass, 1) < G};
@@ -346,66 +404,70 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                     mbar_wait(&sh.w_full[n % tcw::NSTAGE], (n / tcw::NSTAGE) & 1);
                 };
                 auto release = [&](int c) { mma_commit(&sh.w_empty[(nchunk_base + c) % tcw::NSTAGE]); };
-                // K-steps over one 64-wide swizzled K-block (nsteps x 16 columns)
-                auto block = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, int nsteps, uint32_t& accum) {
-                    for (int ks = 0; ks < nsteps; ++ks) {
-                        mma_f16(d, desc_sw128(a + ks * 32), desc_sw128(b + ks * 32), idesc, accum);
-                        accum = 1;
-                    }
+                // NSTEPS K-steps (16 columns each) over one swizzled K-block
+                auto block2 = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t accum) {
+                    const uint64_t da = dsw(a), db = dsw(b);
+                    mma_f16(d, da, db, idesc, accum);
+                    mma_f16(d, da + 2, db + 2, idesc, 1);
+                };
+                auto block4 = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t accum) {
+                    const uint64_t da = dsw(a), db = dsw(b);
+                    mma_f16(d, da, db, idesc, accum);
+                    mma_f16(d, da + 2, db + 2, idesc, 1);
+                    mma_f16(d, da + 4, db + 4, idesc, 1);
+                    mma_f16(d, da + 6, db + 6, idesc, 1);
                 };
                 for (int op = 0; op < 9; ++op) {
                     for (int s = 0; s < 2; ++s) {
                         if (!act[s]) continue;
                         const bool first = (s == 0) || !act[0], last = (s == 1) || !act[1];
-                        mbar_wait(&sh.in_ready[s], par_in[s]); par_in[s] ^= 1;
+                        mbar_wait(&sh.in_ready[s][0], par_in[s]); mbar_wait(&sh.in_ready[s][1], par_in[s]); par_in[s] ^= 1;
                         const uint32_t sl = sbase + s * SLOT_BYTES;
                         const uint32_t d_acc = tmem + s * 256, d_mod = d_acc + 128;
-                        uint32_t accum = 0;
                         if (op == 0) {
                             if (first) { wait_full(0); wait_full(1); }
                             tc_fence_after();
-                            block(d_mod, sl + OFF_MISC, stage_addr(0), ID128, 2, accum);        // modulation (K = 20 + 1)
-                            accum = 0;
-                            block(d_acc, sl + OFF_PE, stage_addr(1), ID128, 4, accum);          // layer 0 (K = 63 + 1)
+                            block2(d_mod, sl + OFF_MISC, stage_addr(0), ID128, 0);               // modulation (K = 20 + 1)
+                            block4(d_acc, sl + OFF_PE, stage_addr(1), ID128, 0);                 // layer 0    (K = 63 + 1)
                             mma_commit(&sh.acc_ready[s]);
                             if (last) { release(0); release(1); }
                         } else if (op <= 4) {                                                    // layers 1..4
                             const int c = 2 * op;
                             if (first) { wait_full(c); wait_full(c + 1); }
                             tc_fence_after();
-                            block(d_acc, sl + OFF_H0, stage_addr(c), ID128, 4, accum);
-                            block(d_acc, sl + OFF_H1, stage_addr(c + 1), ID128, 4, accum);
-                            mma_f16(d_acc, desc_sw128(sl + OFF_MISC + 32), desc_nosw(stage_addr(c + 1) + 16384, 128, 256), ID128, 1);
+                            block4(d_acc, sl + OFF_H0, stage_addr(c), ID128, 0);
+                            block4(d_acc, sl + OFF_H1, stage_addr(c + 1), ID128, 1);
+                            mma_f16(d_acc, dsw(sl + OFF_MISC + 32), dns(stage_addr(c + 1) + 16384), ID128, 1);   // bias step
                             mma_commit(&sh.acc_ready[s]);
                             if (last) { release(c); release(c + 1); }
                         } else if (op == 5) {                                                    // layer 5: [pe | h]
                             if (first) { wait_full(10); wait_full(11); wait_full(12); }
                             tc_fence_after();
-                            block(d_acc, sl + OFF_PE, stage_addr(10), ID128, 4, accum);
-                            block(d_acc, sl + OFF_H0, stage_addr(11), ID128, 4, accum);
-                            block(d_acc, sl + OFF_H1, stage_addr(12), ID128, 4, accum);
+                            block4(d_acc, sl + OFF_PE, stage_addr(10), ID128, 0);
+                            block4(d_acc, sl + OFF_H0, stage_addr(11), ID128, 1);
+                            block4(d_acc, sl + OFF_H1, stage_addr(12), ID128, 1);
                             mma_commit(&sh.acc_ready[s]);
                             if (last) { release(10); release(11); release(12); }
-                        } else if (op == 6) {                                                    // feature (128) + sigma
+                        } else if (op == 6) {                                                    // feature (128) + sigma (col 128)
                             if (first) { wait_full(13); wait_full(14); }
                             tc_fence_after();
-                            block(d_acc, sl + OFF_H0, stage_addr(13), ID144, 4, accum);
-                            block(d_acc, sl + OFF_H1, stage_addr(14), ID144, 4, accum);
-                            mma_f16(d_acc, desc_sw128(sl + OFF_MISC + 32), desc_nosw(stage_addr(14) + 18432, 128, 256), ID144, 1);
+                            block4(d_acc, sl + OFF_H0, stage_addr(13), ID144, 0);
+                            block4(d_acc, sl + OFF_H1, stage_addr(14), ID144, 1);
+                            mma_f16(d_acc, dsw(sl + OFF_MISC + 32), dns(stage_addr(14) + 18432), ID144, 1);
                             mma_commit(&sh.acc_ready[s]);
                             if (last) { release(13); release(14); }
                         } else if (op == 7) {                                                    // views: [feature | dir]
                             if (first) { wait_full(15); wait_full(16); }
                             tc_fence_after();
-                            block(d_acc, sl + OFF_H0, stage_addr(15), ID64, 4, accum);
-                            block(d_acc, sl + OFF_H1, stage_addr(16), ID64, 4, accum);
-                            mma_f16(d_acc, desc_sw128(sl + OFF_MISC + 64), desc_nosw(stage_addr(16) + 8192, 128, 256), ID64, 1);
+                            block4(d_acc, sl + OFF_H0, stage_addr(15), ID64, 0);
+                            block4(d_acc, sl + OFF_H1, stage_addr(16), ID64, 1);
+                            mma_f16(d_acc, dsw(sl + OFF_MISC + 64), dns(stage_addr(16) + 8192), ID64, 1);
                             mma_commit(&sh.acc_ready[s]);
                             if (last) { release(15); release(16); }
                         } else {                                                                 // rgb (N = 16, 3 used)
                             if (first) wait_full(17);
                             tc_fence_after();
-                            block(d_acc, sl + OFF_H0, stage_addr(17), ID16, 4, accum);
+                            block4(d_acc, sl + OFF_H0, stage_addr(17), ID16, 0);
                             mma_commit(&sh.acc_ready[s]);
                             if (last) release(17);
                         }
@@ -432,7 +494,7 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem, 512);
+    if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
 int launch_render_tc(const SceneDev& sc, const RenderIO& io, bool fast, const void* wimg, cudaStream_t stream) {

@@ -59,7 +59,7 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
 // K-major operand tile stored as 64-element (128-byte) rows, 8-row groups 1024 B apart, 16-byte
 // chunks XOR-swizzled by (row % 8): the SWIZZLE_128B canonical layout.  The tile base must be
 // 1024-byte aligned; a K-step of 16 elements advances the start address by 32 bytes.
-__device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
+__host__ __device__ constexpr uint64_t desc_sw128(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);            // start address
     d |= (uint64_t)1 << 16;                            // leading byte offset (ignored for swizzled K-major)
@@ -70,7 +70,7 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
 }
 // K-major, no swizzle: 8x16-byte core matrices; lbo = byte distance between the two K halves of a
 // 16-element K-step, sbo = byte distance between consecutive 8-row groups.
-__device__ __forceinline__ uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+__host__ __device__ constexpr uint64_t desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;

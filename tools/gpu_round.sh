@@ -10,7 +10,7 @@ python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=
 tail -5 $OUT/pytest_gpu.log
 python bench.py --steps 10 --warmup 3 --mode $MODE > $OUT/bench_$MODE.json 2> $OUT/bench_$MODE.err; echo "bench rc=$?"
 tail -c 3000 $OUT/bench_$MODE.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_$MODE.csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches_$MODE.csv \
     python bench.py --steps 2 --warmup 3 --mode $MODE --no-cpu-baseline > $OUT/ncu_launch_run.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:render_ -s 3 -c 1 -o $OUT/render_$MODE \
     python bench.py --steps 1 --warmup 3 --mode $MODE --no-cpu-baseline > $OUT/ncu_full_run.log 2>&1
