@@ -102,6 +102,8 @@ __global__ void pack_mlp_fp32_kernel(MlpPtrs w, float* __restrict__ out) {
     copy_into(out + BR, w.p[I_BR], 3, 4, tid, nt);
 }
 
+static long long* g_trace = nullptr;
+
 static int make_scene(const mvsn_render_scene* s, SceneDev& d) {
     MVSN_REQUIRE(s != nullptr, MVSN_ENULL, "scene is NULL");
     MVSN_REQUIRE(s->volume_dhwc && s->imgs_hwc4 && s->mlp_packed, MVSN_ENULL, "scene has a NULL buffer");
@@ -138,6 +140,7 @@ extern "C" {
 
 const char* mvsn_last_error(void) { return g_err; }
 int mvsn_abi_version(void) { return 1; }
+void mvsn_debug_set_trace(long long* device_buffer) { g_trace = device_buffer; }
 
 size_t mvsn_mlp_packed_bytes(int mode) {
     switch (mode) {
@@ -212,6 +215,7 @@ int mvsn_render_samples(const mvsn_render_scene* scene, const float* rays_pts, c
     io.pts = rays_pts; io.ndc = rays_ndc; io.z = z_vals; io.dirs = rays_dir;
     io.N = N; io.S = S;
     io.rgb = rgb; io.depth = depth; io.weights = weights; io.alpha = alpha; io.input_feat = input_feat;
+    io.trace = g_trace;
     return dispatch_render(scene, sc, io, false, (cudaStream_t)stream);
 }
 
@@ -240,6 +244,7 @@ int mvsn_render_rays(const mvsn_render_scene* scene, const mvsn_ray_params* rp, 
     io.rg.wf = (float)scene->W / 4.0f;     // (inv_scale + 1) / 4, utils.py:139
     io.rg.hf = (float)scene->H / 4.0f;
     io.rg.lindisp = rp->lindisp;
+    io.trace = g_trace;
     return dispatch_render(scene, sc, io, true, (cudaStream_t)stream);
 }
 

@@ -57,7 +57,7 @@ __global__ void feats_to_cl_kernel(const float* __restrict__ src, float* __restr
 }
 
 struct Taps {              // bilinear taps of one source view for one voxel (zeros padding)
-    int off[4];            // pixel index (y*w + x) of nw, ne, sw, se; -1 when outside
+    int off[4];            // pixel index (y*w + x) of nw, ne, sw, se (clamped; weight 0 when outside)
     float wgt[4];
     float mask;
 };
@@ -80,11 +80,13 @@ __device__ __forceinline__ Taps make_taps(const float* __restrict__ P, float xr,
     if (!(ix == ix) || !(iy == iy)) { x0 = -2; y0 = -2; }                       // NaN: no contribution
     const bool vx0 = (unsigned)x0 < (unsigned)w, vx1 = (unsigned)(x0 + 1) < (unsigned)w;
     const bool vy0 = (unsigned)y0 < (unsigned)h, vy1 = (unsigned)(y0 + 1) < (unsigned)h;
-    t.off[0] = (vx0 && vy0) ? y0 * w + x0 : -1;
-    t.off[1] = (vx1 && vy0) ? y0 * w + x0 + 1 : -1;
-    t.off[2] = (vx0 && vy1) ? (y0 + 1) * w + x0 : -1;
-    t.off[3] = (vx1 && vy1) ? (y0 + 1) * w + x0 + 1 : -1;
-    t.wgt[0] = wx0 * wy0; t.wgt[1] = wx1 * wy0; t.wgt[2] = wx0 * wy1; t.wgt[3] = wx1 * wy1;
+    // every tap is loaded unconditionally (clamped address) with weight 0 when it falls outside:
+    // the eight 16-byte loads per channel group are then in flight together
+    const int xc0 = min(max(x0, 0), w - 1), xc1 = min(max(x0 + 1, 0), w - 1);
+    const int yc0 = min(max(y0, 0), h - 1), yc1 = min(max(y0 + 1, 0), h - 1);
+    t.off[0] = yc0 * w + xc0; t.off[1] = yc0 * w + xc1; t.off[2] = yc1 * w + xc0; t.off[3] = yc1 * w + xc1;
+    t.wgt[0] = (vx0 && vy0) ? wx0 * wy0 : 0.f; t.wgt[1] = (vx1 && vy0) ? wx1 * wy0 : 0.f;
+    t.wgt[2] = (vx0 && vy1) ? wx0 * wy1 : 0.f; t.wgt[3] = (vx1 && vy1) ? wx1 * wy1 : 0.f;
     return t;
 }
 
@@ -121,11 +123,9 @@ cost_volume_kernel(const CostArgs a) {
             float cr = 0.f, cg = 0.f, cb = 0.f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (t[v - 1].off[k] >= 0) {
-                    float4 p = __ldg(a.small + (size_t)v * hw + t[v - 1].off[k]);
-                    cr = fmaf(p.x, t[v - 1].wgt[k], cr); cg = fmaf(p.y, t[v - 1].wgt[k], cg);
-                    cb = fmaf(p.z, t[v - 1].wgt[k], cb);
-                }
+                float4 p = __ldg(a.small + (size_t)v * hw + t[v - 1].off[k]);
+                cr = fmaf(p.x, t[v - 1].wgt[k], cr); cg = fmaf(p.y, t[v - 1].wgt[k], cg);
+                cb = fmaf(p.z, t[v - 1].wgt[k], cb);
             }
             out[(size_t)(3 * v + 0) * nvox] = cr; out[(size_t)(3 * v + 1) * nvox] = cg;
             out[(size_t)(3 * v + 2) * nvox] = cb;
@@ -145,12 +145,10 @@ cost_volume_kernel(const CostArgs a) {
                 const float4* fv = reinterpret_cast<const float4*>(a.feats_cl + (size_t)v * hw * 32) + g;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (t[v - 1].off[k] >= 0) {
-                        float4 p = __ldg(fv + (size_t)t[v - 1].off[k] * 8);
-                        const float wk = t[v - 1].wgt[k];
-                        wv[0] = fmaf(p.x, wk, wv[0]); wv[1] = fmaf(p.y, wk, wv[1]);
-                        wv[2] = fmaf(p.z, wk, wv[2]); wv[3] = fmaf(p.w, wk, wv[3]);
-                    }
+                    float4 p = __ldg(fv + (size_t)t[v - 1].off[k] * 8);
+                    const float wk = t[v - 1].wgt[k];
+                    wv[0] = fmaf(p.x, wk, wv[0]); wv[1] = fmaf(p.y, wk, wv[1]);
+                    wv[2] = fmaf(p.z, wk, wv[2]); wv[3] = fmaf(p.w, wk, wv[3]);
                 }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {

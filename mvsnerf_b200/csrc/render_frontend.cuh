@@ -40,7 +40,9 @@ struct RenderIO {
     const float* rays; const float* t_steps;
     RayGenDev rg;
     int N, S;
+    int rays_per_tile;     // tensor-core kernel: chosen by its launcher
     float* rgb; float* depth; float* weights; float* alpha; float* input_feat;
+    long long* trace;      // debug timeline (mvsn_debug_set_trace), null in normal operation
 };
 
 int launch_render_fp32(const SceneDev& sc, const RenderIO& io, bool fast, const float* wts, cudaStream_t stream);
@@ -49,6 +51,12 @@ size_t mlp_tc_packed_bytes();
 int pack_mlp_tc(const float* const* w, void* packed, cudaStream_t stream);
 
 // cam = R p + t ; pix = K cam ; (u, v) = pix.xy / pix.z / (W-1, H-1)     utils.py:120-127
+template <bool PRECISE>
+__device__ __forceinline__ float fdiv(float a, float b) { return PRECISE ? __fdiv_rn(a, b) : __fdividef(a, b); }
+
+// PRECISE = IEEE divisions exactly where the reference divides (fp32-parity modes); otherwise
+// MUFU.RCP-based divisions (2 ulp), plenty for the 16-bit-operand mode and a fraction of the code.
+template <bool PRECISE = true>
 __device__ __forceinline__ void project_view(const float* __restrict__ w2c, const float* __restrict__ K,
                                              float px, float py, float pz, float wm1, float hm1,
                                              float& u, float& v, float& zc) {
@@ -58,75 +66,83 @@ __device__ __forceinline__ void project_view(const float* __restrict__ w2c, cons
     float qx = fmaf(cz, K[2], fmaf(cy, K[1], cx * K[0]));
     float qy = fmaf(cz, K[5], fmaf(cy, K[4], cx * K[3]));
     float qz = fmaf(cz, K[8], fmaf(cy, K[7], cx * K[6]));
-    u = __fdiv_rn(__fdiv_rn(qx, qz), wm1);
-    v = __fdiv_rn(__fdiv_rn(qy, qz), hm1);
+    if (PRECISE) {
+        u = __fdiv_rn(__fdiv_rn(qx, qz), wm1);
+        v = __fdiv_rn(__fdiv_rn(qy, qz), hm1);
+    } else {
+        const float iz = __fdividef(1.f, qz);
+        u = qx * iz * __fdividef(1.f, wm1);
+        v = qy * iz * __fdividef(1.f, hm1);
+    }
     zc = qz;
 }
 
 // utils.get_ndc_coordinate for the reference camera (utils.py:112-146)
+template <bool PRECISE = true>
 __device__ __forceinline__ void ndc_of_point(const SceneDev& sc, const Cams& cams, const RayGenDev& rg,
                                              float px, float py, float pz,
                                              float& nx, float& ny, float& nz) {
     float u, v, zc;
-    project_view(cams.w2c[0], cams.K[0], px, py, pz, (float)(sc.W - 1), (float)(sc.H - 1), u, v, zc);
-    if (!rg.lindisp) nz = __fdiv_rn(zc - rg.near, rg.far_minus_near);
-    else             nz = __fdiv_rn(__fdiv_rn(1.0f, zc) - rg.inv_near, rg.inv_far_minus_inv_near);
+    project_view<PRECISE>(cams.w2c[0], cams.K[0], px, py, pz, (float)(sc.W - 1), (float)(sc.H - 1), u, v, zc);
+    if (!rg.lindisp) nz = fdiv<PRECISE>(zc - rg.near, rg.far_minus_near);
+    else             nz = fdiv<PRECISE>(fdiv<PRECISE>(1.0f, zc) - rg.inv_near, rg.inv_far_minus_inv_near);
     if (rg.pad > 0.f) {
         float dh = rg.hf + rg.pad * 2.f, dw = rg.wf + rg.pad * 2.f;
-        v = __fadd_rn(__fdiv_rn(__fmul_rn(v, rg.hf), dh), __fdiv_rn(rg.pad, dh));
-        u = __fadd_rn(__fdiv_rn(__fmul_rn(u, rg.wf), dw), __fdiv_rn(rg.pad, dw));
+        v = __fadd_rn(fdiv<PRECISE>(__fmul_rn(v, rg.hf), dh), fdiv<PRECISE>(rg.pad, dh));
+        u = __fadd_rn(fdiv<PRECISE>(__fmul_rn(u, rg.wf), dw), fdiv<PRECISE>(rg.pad, dw));
     }
     nx = u; ny = v;
 }
 
-// utils.index_point_feature (utils.py:357-383): trilinear, zeros padding, align_corners=True
+// utils.index_point_feature (utils.py:357-383): trilinear, zeros padding, align_corners=True.
+// All sixteen 16-byte loads are issued unconditionally (indices clamped, out-of-volume corners get
+// weight 0) so they are in flight together instead of one DRAM latency per corner.
 __device__ __forceinline__ void sample_volume(const SceneDev& sc, float nx, float ny, float nz, float* out8) {
     const int W = sc.Wp, H = sc.Hp, D = sc.D;
     float ix = ((nx * 2.f - 1.f + 1.f) * 0.5f) * (float)(W - 1);
     float iy = ((ny * 2.f - 1.f + 1.f) * 0.5f) * (float)(H - 1);
     float iz = ((nz * 2.f - 1.f + 1.f) * 0.5f) * (float)(D - 1);
     float x0f = floorf(ix), y0f = floorf(iy), z0f = floorf(iz);
-    float wx1 = ix - x0f, wy1 = iy - y0f, wz1 = iz - z0f;
-    float wx0 = (x0f + 1.f) - ix, wy0 = (y0f + 1.f) - iy, wz0 = (z0f + 1.f) - iz;
+    float wx[2] = {(x0f + 1.f) - ix, ix - x0f}, wy[2] = {(y0f + 1.f) - iy, iy - y0f}, wz[2] = {(z0f + 1.f) - iz, iz - z0f};
     // clamp before the int conversion so absurd coordinates cannot overflow
-    int x0 = (int)fminf(fmaxf(x0f, -2.f), (float)W);
-    int y0 = (int)fminf(fmaxf(y0f, -2.f), (float)H);
-    int z0 = (int)fminf(fmaxf(z0f, -2.f), (float)D);
+    const int x0 = (int)fminf(fmaxf(x0f, -2.f), (float)W);
+    const int y0 = (int)fminf(fmaxf(y0f, -2.f), (float)H);
+    const int z0 = (int)fminf(fmaxf(z0f, -2.f), (float)D);
+    int xo[2], yo[2], zo[2];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        const int x = x0 + d, y = y0 + d, z = z0 + d;
+        if ((unsigned)x >= (unsigned)W) wx[d] = 0.f;       // zeros padding: the tap contributes nothing
+        if ((unsigned)y >= (unsigned)H) wy[d] = 0.f;
+        if ((unsigned)z >= (unsigned)D) wz[d] = 0.f;
+        xo[d] = min(max(x, 0), W - 1); yo[d] = min(max(y, 0), H - 1); zo[d] = min(max(z, 0), D - 1);
+    }
+    float4 va[8], vb[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4* p = reinterpret_cast<const float4*>(
+            sc.vol + (((size_t)zo[c >> 2] * H + yo[(c >> 1) & 1]) * W + xo[c & 1]) * 8);
+        va[c] = __ldg(p); vb[c] = __ldg(p + 1);
+    }
 #pragma unroll
     for (int c = 0; c < 8; ++c) out8[c] = 0.f;
 #pragma unroll
-    for (int dz = 0; dz < 2; ++dz) {
-        int z = z0 + dz;
-        float wz = dz ? wz1 : wz0;
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy) {
-            int y = y0 + dy;
-            float wy = dy ? wy1 : wy0;
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-                int x = x0 + dx;
-                float wx = dx ? wx1 : wx0;
-                if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H && (unsigned)z < (unsigned)D) {
-                    const float4* p = reinterpret_cast<const float4*>(
-                        sc.vol + (((size_t)z * H + y) * W + x) * 8);
-                    float4 a = __ldg(p), b = __ldg(p + 1);
-                    float wgt = wx * wy * wz;
-                    out8[0] = fmaf(a.x, wgt, out8[0]); out8[1] = fmaf(a.y, wgt, out8[1]);
-                    out8[2] = fmaf(a.z, wgt, out8[2]); out8[3] = fmaf(a.w, wgt, out8[3]);
-                    out8[4] = fmaf(b.x, wgt, out8[4]); out8[5] = fmaf(b.y, wgt, out8[5]);
-                    out8[6] = fmaf(b.z, wgt, out8[6]); out8[7] = fmaf(b.w, wgt, out8[7]);
-                }
-            }
-        }
+    for (int c = 0; c < 8; ++c) {                          // accumulation order as aten: x fastest, then y, then z
+        const float wgt = wx[c & 1] * wy[(c >> 1) & 1] * wz[c >> 2];
+        out8[0] = fmaf(va[c].x, wgt, out8[0]); out8[1] = fmaf(va[c].y, wgt, out8[1]);
+        out8[2] = fmaf(va[c].z, wgt, out8[2]); out8[3] = fmaf(va[c].w, wgt, out8[3]);
+        out8[4] = fmaf(vb[c].x, wgt, out8[4]); out8[5] = fmaf(vb[c].y, wgt, out8[5]);
+        out8[6] = fmaf(vb[c].z, wgt, out8[6]); out8[7] = fmaf(vb[c].w, wgt, out8[7]);
     }
 }
 
 // utils.build_color_volume (utils.py:300-332): bilinear, BORDER padding, strict in-bounds mask.
 // out4 = (r, g, b, mask)
+template <bool PRECISE = true>
 __device__ __forceinline__ void sample_color(const SceneDev& sc, const Cams& cams, int v, float px, float py, float pz, float* out4) {
     const int W = sc.W, H = sc.H;
     float u, vv, zc;
-    project_view(cams.w2c[v], cams.K[v], px, py, pz, (float)(W - 1), (float)(H - 1), u, vv, zc);
+    project_view<PRECISE>(cams.w2c[v], cams.K[v], px, py, pz, (float)(W - 1), (float)(H - 1), u, vv, zc);
     float gx = u * 2.f - 1.f, gy = vv * 2.f - 1.f;
     float ix = ((gx + 1.f) * 0.5f) * (float)(W - 1);
     float iy = ((gy + 1.f) * 0.5f) * (float)(H - 1);
@@ -149,9 +165,15 @@ __device__ __forceinline__ void sample_color(const SceneDev& sc, const Cams& cam
 }
 
 // gen_dir_feature (renderer.py:111-122,142-147): unit direction in the reference camera frame
+template <bool PRECISE = true>
 __device__ __forceinline__ void view_dir(const Cams& cams, float dx, float dy, float dz, float* out3) {
-    float n = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
-    dx = __fdiv_rn(dx, n); dy = __fdiv_rn(dy, n); dz = __fdiv_rn(dz, n);
+    if (PRECISE) {
+        float n = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        dx = __fdiv_rn(dx, n); dy = __fdiv_rn(dy, n); dz = __fdiv_rn(dz, n);
+    } else {
+        const float rn = rsqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+        dx *= rn; dy *= rn; dz *= rn;
+    }
     const float* R = cams.w2c[0];
     out3[0] = fmaf(dz, R[2], fmaf(dy, R[1], dx * R[0]));
     out3[1] = fmaf(dz, R[6], fmaf(dy, R[5], dx * R[4]));

@@ -38,7 +38,7 @@ __host__ __device__ constexpr int chunk_offset(int c) {
 constexpr int STREAM_BYTES = chunk_offset(NCHUNK);          // 291 328
 constexpr int TAIL_OFFSET = STREAM_BYTES;                   // fp32 tail: rgb_linear.bias[3], 0
 constexpr int TOTAL_BYTES = STREAM_BYTES + 16;
-constexpr int STAGE_BYTES = 24576;
+constexpr int STAGE_BYTES = 23552;                          // >= largest chunk (23 040), 1024-aligned
 constexpr int NSTAGE = 4;
 }  // namespace tcw
 
@@ -46,16 +46,15 @@ constexpr int TC_THREADS = 576;                           // 16 slot warps + MMA
 constexpr int SLOT_BYTES = 65536;                           // PE 16K | H0 16K | H1 16K | MISC 16K
 constexpr int OFF_PE = 0, OFF_H0 = 16384, OFF_H1 = 32768, OFF_MISC = 49152;
 constexpr int RING_OFFSET = 2 * SLOT_BYTES;
-constexpr int TC_SMEM_BYTES = RING_OFFSET + tcw::NSTAGE * tcw::STAGE_BYTES + 1024;
+constexpr int XCH_OFFSET = RING_OFFSET + tcw::NSTAGE * tcw::STAGE_BYTES;   // per slot: float4 (alpha, r, g, b) x 128 rows
+constexpr int TC_SMEM_BYTES = XCH_OFFSET + 2 * 2048 + 1024;
 
 struct TcShared {
-    uint64_t in_ready[2][2];    // slot group part (128 arrivals each) -> MMA issuer: operand columns written
+    uint64_t in_ready[2];       // slot group (256 arrivals) -> MMA issuer: operand tile written
     uint64_t acc_ready[2];      // tcgen05.commit -> slot group: accumulator complete
     uint64_t w_full[tcw::NSTAGE];
-    uint64_t w_empty[tcw::NSTAGE];
+    uint64_t w_free;            // one phase per GEMM op: its weight chunks may be overwritten
     uint32_t tmem_base;
-    float scan[2][4][8];        // per slot, per warp: cross-warp compositing scratch
-    float carry[2][8];          // S > 128: transmittance / partial sums carried between chunks
     Cams cams;
 };
 
@@ -109,6 +108,27 @@ __device__ __forceinline__ void epilogue(uint32_t t_acc, uint32_t t_mod, uint8_t
     }
 }
 
+// ---- GEMM schedule of one tile (op = one accumulator phase) --------------------------------------
+// op 0: modulation (MISC x chunk 0 -> TMEM cols 128..) + layer 0 (PE x chunk 1); ops 1-4: layers 1-4;
+// op 5: layer 5 [PE | H]; op 6: feature + sigma (N = 144); op 7: views layer (N = 64); op 8: rgb (N = 16)
+__constant__ int c_op_nblk[9] = {2, 2, 2, 2, 2, 3, 2, 2, 1};
+__constant__ uint32_t c_op_idesc[9] = {idesc_f16(128, 128), idesc_f16(128, 128), idesc_f16(128, 128), idesc_f16(128, 128),
+                                       idesc_f16(128, 128), idesc_f16(128, 128), idesc_f16(128, 144), idesc_f16(128, 64),
+                                       idesc_f16(128, 16)};
+__constant__ int c_blk_chunk[9][3] = {{0, 1, 0}, {2, 3, 0}, {4, 5, 0}, {6, 7, 0}, {8, 9, 0}, {10, 11, 12}, {13, 14, 0}, {15, 16, 0}, {17, 0, 0}};
+__constant__ uint32_t c_blk_aoff[9][3] = {{49152, 0, 0}, {16384, 32768, 0}, {16384, 32768, 0}, {16384, 32768, 0}, {16384, 32768, 0},
+                                          {0, 16384, 32768}, {16384, 32768, 0}, {16384, 32768, 0}, {16384, 0, 0}};
+__constant__ int c_chunk_op[18] = {0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 5, 6, 6, 7, 7, 8};
+__constant__ uint32_t c_op_bias_aoff[9] = {0, 49152 + 32, 49152 + 32, 49152 + 32, 49152 + 32, 0, 49152 + 32, 49152 + 64, 0};
+__constant__ uint32_t c_op_bias_boff[9] = {0, 16384, 16384, 16384, 16384, 0, 18432, 8192, 0};
+
+// debug timeline: role r writes (clock << 8 | event) into trace[r * 1024 + i]
+#ifdef MVSN_TC_TRACE
+#define TC_TRACE(ev) do { if (tr && tr_n < 1023) tr[tr_n++] = (clock64() << 8) | (long long)(ev); } while (0)
+#else
+#define TC_TRACE(ev) do { } while (0)
+#endif
+
 template <bool FAST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict__ wimg) {
@@ -120,10 +140,11 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
     load_cams(sc, &sh.cams, tid);
     if (tid == 0) {
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&sh.in_ready[s][0], 128); mbar_init(&sh.in_ready[s][1], 128);
+            mbar_init(&sh.in_ready[s], 256);
             mbar_init(&sh.acc_ready[s], 1);
         }
-        for (int i = 0; i < tcw::NSTAGE; ++i) { mbar_init(&sh.w_full[i], 1); mbar_init(&sh.w_empty[i], 1); }
+        for (int i = 0; i < tcw::NSTAGE; ++i) mbar_init(&sh.w_full[i], 1);
+        mbar_init(&sh.w_free, 1);
         fence_barrier_init();
     }
     if (warp == 16) { tmem_alloc(&sh.tmem_base, 512); tmem_relinquish(); }
@@ -131,16 +152,27 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sh.tmem_base;
+    // trace roles: 0..3 = (slot, part) warp 0 lane 0 ; 4 = MMA issuer ; 5 = loader
+    long long* tr = nullptr; int tr_n = 0;
+    if (io.trace && blockIdx.x == 0 && lane == 0) {
+        if (warp < 16 && (warp & 3) == 0) tr = io.trace + (warp >> 2) * 1024;
+        else if (warp >= 16) tr = io.trace + (4 + warp - 16) * 1024;
+    }
 
     // ---- work decomposition (identical in every role) ---------------------------------------------
     const int N = io.N, S = io.S;
-    const int R = S <= 128 ? 128 / S : 1;                    // rays per tile (S | 128 or 128 | S)
-    const int nchunks = S <= 128 ? 1 : S / 128;
-    const int G = (N + R - 1) / R;                           // ray groups
+    // A tile is RT rays x SP = 128/RT consecutive samples: row = sub * RT + ray_in, so the 32 lanes of a
+    // warp are (for RT = 32) adjacent rays at the SAME sample index -- their volume / image taps fall in
+    // the same few cache lines.  A slot walks the NT tiles of its RT-ray group front to back and the
+    // compositing state (transmittance, sums) is carried in registers.  Any S works.
+    const int RT = io.rays_per_tile, SP = 128 / RT;
+    const int rt_shift = 31 - __clz(RT);
+    const int NT = (S + SP - 1) / SP;                        // tiles (= passes) per ray group
+    const int G = (N + RT - 1) / RT;                         // ray groups
     const int pairs_total = (G + 1) / 2;
     const int my_pairs = blockIdx.x < pairs_total ? (pairs_total - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int npass = my_pairs * nchunks;                    // one tile per active slot per pass
-    auto group_of = [&](int pass, int s) { return ((pass / nchunks) * (int)gridDim.x + (int)blockIdx.x) * 2 + s; };
+    const int npass = my_pairs * NT;                         // one tile per active slot per pass
+    auto group_of = [&](int pass, int s) { return ((pass / NT) * (int)gridDim.x + (int)blockIdx.x) * 2 + s; };
 
     if (warp < 16) {
         // =========================== slot group: front end + epilogues + compositing ===============
@@ -151,6 +183,7 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
         const uint32_t t_acc = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(s * 256);
         const uint32_t t_mod = t_acc + 128;
         uint32_t par_acc = 0, par_op8 = 0;
+        float cT = 1.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f;   // compositing state of ray `row` (row < RT)
         bool pending_op8 = false;                            // part 1 skips the op-8 wait; it is made up before the next arrive
         const float br0 = __ldg(reinterpret_cast<const float*>(wimg + tcw::TAIL_OFFSET));
         const float br1 = __ldg(reinterpret_cast<const float*>(wimg + tcw::TAIL_OFFSET) + 1);
@@ -158,13 +191,13 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
         uint8_t* hblk = slot + (part ? OFF_H1 : OFF_H0);
 
         for (int pass = 0; pass < npass; ++pass) {
-            const int g = group_of(pass, s), chunk = pass % nchunks;
+            const int g = group_of(pass, s), tile = pass % NT;
             if (g >= G) continue;                            // this slot idles in the last pass
+            TC_TRACE(1);
             // -------------------------- front end -------------------------------------------------
-            int r_in, s_idx;
-            if (S <= 128) { r_in = row / S; s_idx = row - r_in * S; } else { r_in = 0; s_idx = chunk * 128 + row; }
-            const int ray = g * R + r_in;
-            const bool valid = ray < N;
+            const int r_in = row & (RT - 1), s_idx = tile * SP + (row >> rt_shift);
+            const int ray = g * RT + r_in;
+            const bool valid = ray < N && s_idx < S;
             const size_t si = (size_t)ray * S + s_idx;
             float nx = 0.f, ny = 0.f, nz = 0.f, zv = 0.f;
             float px = 0.f, py = 0.f, pz = 0.f, dx = 0.f, dy = 0.f, dz = 1.f;
@@ -180,7 +213,7 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                     px = __fadd_rn(r0.x, __fmul_rn(dx, zv));
                     py = __fadd_rn(r0.y, __fmul_rn(dy, zv));
                     pz = __fadd_rn(r0.z, __fmul_rn(dz, zv));
-                    ndc_of_point(sc, sh.cams, io.rg, px, py, pz, nx, ny, nz);
+                    ndc_of_point<false>(sc, sh.cams, io.rg, px, py, pz, nx, ny, nz);
                 } else {
                     px = __ldg(io.pts + si * 3); py = __ldg(io.pts + si * 3 + 1); pz = __ldg(io.pts + si * 3 + 2);
                     nx = __ldg(io.ndc + si * 3); ny = __ldg(io.ndc + si * 3 + 1); nz = __ldg(io.ndc + si * 3 + 2);
@@ -190,21 +223,10 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                 }
             }
             const float nd[3] = {nx, ny, nz};
+            TC_TRACE(3);
             if (part == 0) {
-                // volume features (8) -> MISC cols 0..7 ; PE cols 0..31 = [x y z | sin(2^k x) for 29 of 30]
-                float feat[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) feat[i] = 0.f;
-                if (valid) {
-                    sample_volume(sc, nx, ny, nz, feat);
-                    if (io.input_feat) {
-                        float4* o = reinterpret_cast<float4*>(io.input_feat + si * 20);
-                        o[0] = make_float4(feat[0], feat[1], feat[2], feat[3]);
-                        o[1] = make_float4(feat[4], feat[5], feat[6], feat[7]);
-                    }
-                }
-                *reinterpret_cast<uint4*>(slot + OFF_MISC + sw128_offset(row, 0)) =
-                    make_uint4(pack_h2(feat[0], feat[1]), pack_h2(feat[2], feat[3]), pack_h2(feat[4], feat[5]), pack_h2(feat[6], feat[7]));
+                // PE cols 0..31 = [x y z | sin(2^k x) for the first 29 of 30].  (part 0 also owns the rgb
+                // epilogue + compositing of the previous tile, so it gets the light half of the front end)
                 float v[32];
                 v[0] = nx; v[1] = ny; v[2] = nz;
                 float f = 1.f;
@@ -221,30 +243,36 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                         make_uint4(pack_h2(v[c * 8], v[c * 8 + 1]), pack_h2(v[c * 8 + 2], v[c * 8 + 3]),
                                    pack_h2(v[c * 8 + 4], v[c * 8 + 5]), pack_h2(v[c * 8 + 6], v[c * 8 + 7]));
             } else {
-                // colour features (12) + view direction -> MISC cols 8..47 ; PE cols 32..63 = [sin(512 z) | cos | 1]
-                float feat[12], dir[3] = {0.f, 0.f, 0.f};
+                // all gathers: volume (8) + colour (12) features + view direction -> MISC cols 0..47 ;
+                // PE cols 32..63 = [sin(512 z) | cos | 1].  This half starts while part 0 is still compositing.
+                float feat[20], dir[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-                for (int i = 0; i < 12; ++i) feat[i] = 0.f;
+                for (int i = 0; i < 20; ++i) feat[i] = 0.f;
                 if (valid) {
-                    view_dir(sh.cams, dx, dy, dz, dir);
+                    view_dir<false>(sh.cams, dx, dy, dz, dir);
+                    sample_volume(sc, nx, ny, nz, feat);
 #pragma unroll
-                    for (int v = 0; v < 3; ++v) sample_color(sc, sh.cams, v, px, py, pz, feat + 4 * v);
+                    for (int v = 0; v < 3; ++v) sample_color<false>(sc, sh.cams, v, px, py, pz, feat + 8 + 4 * v);
                     if (io.input_feat) {
-                        float4* o = reinterpret_cast<float4*>(io.input_feat + si * 20) + 2;
-                        o[0] = make_float4(feat[0], feat[1], feat[2], feat[3]);
-                        o[1] = make_float4(feat[4], feat[5], feat[6], feat[7]);
-                        o[2] = make_float4(feat[8], feat[9], feat[10], feat[11]);
+                        float4* o = reinterpret_cast<float4*>(io.input_feat + si * 20);
+#pragma unroll
+                        for (int i = 0; i < 5; ++i)
+                            o[i] = make_float4(feat[4 * i], feat[4 * i + 1], feat[4 * i + 2], feat[4 * i + 3]);
                     }
                 }
+                TC_TRACE(4);
                 uint8_t* m = slot + OFF_MISC;
-                *reinterpret_cast<uint4*>(m + sw128_offset(row, 8)) =
+                *reinterpret_cast<uint4*>(m + sw128_offset(row, 0)) =
                     make_uint4(pack_h2(feat[0], feat[1]), pack_h2(feat[2], feat[3]), pack_h2(feat[4], feat[5]), pack_h2(feat[6], feat[7]));
+                *reinterpret_cast<uint4*>(m + sw128_offset(row, 8)) =
+                    make_uint4(pack_h2(feat[8], feat[9]), pack_h2(feat[10], feat[11]), pack_h2(feat[12], feat[13]), pack_h2(feat[14], feat[15]));
                 *reinterpret_cast<uint4*>(m + sw128_offset(row, 16)) =
-                    make_uint4(pack_h2(feat[8], feat[9]), pack_h2(feat[10], feat[11]), pack_h2(1.f, 0.f), 0u);
+                    make_uint4(pack_h2(feat[16], feat[17]), pack_h2(feat[18], feat[19]), pack_h2(1.f, 0.f), 0u);
                 *reinterpret_cast<uint4*>(m + sw128_offset(row, 24)) = make_uint4(0u, 0u, 0u, 0u);
                 *reinterpret_cast<uint4*>(m + sw128_offset(row, 32)) =
                     make_uint4(pack_h2(dir[0], dir[1]), pack_h2(dir[2], 1.f), 0u, 0u);
                 *reinterpret_cast<uint4*>(m + sw128_offset(row, 40)) = make_uint4(0u, 0u, 0u, 0u);
+                TC_TRACE(5);
                 float v[32];
                 v[0] = __sinf(nz * 512.f);
                 float f = 1.f;
@@ -262,18 +290,21 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                                    pack_h2(v[c * 8 + 4], v[c * 8 + 5]), pack_h2(v[c * 8 + 6], v[c * 8 + 7]));
             }
             fence_proxy_async();
+            TC_TRACE(2);
             if (pending_op8) { mbar_wait(&sh.acc_ready[s], par_op8); pending_op8 = false; }   // previous tile's op 8 retired
-            mbar_arrive(&sh.in_ready[s][part]);
+            mbar_arrive(&sh.in_ready[s]);
 
             // -------------------------- trunk: ops 0..5 -> h ------------------------------------------
 #pragma unroll 1
             for (int op = 0; op < 6; ++op) {
                 mbar_wait(&sh.acc_ready[s], par_acc); par_acc ^= 1;
+                TC_TRACE(10 + op);
                 tc_fence_after();
                 epilogue<64, true, true>(t_acc + part * 64, t_mod + part * 64, hblk, row, 0);
                 tc_fence_before();
                 fence_proxy_async();
-                mbar_arrive(&sh.in_ready[s][part]);
+                TC_TRACE(30 + op);
+                mbar_arrive(&sh.in_ready[s]);
             }
             // -------------------------- op 6: feature (128) + sigma (col 128) ---------------------------
             float sigma = 0.f;
@@ -289,7 +320,7 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                 }
                 tc_fence_before();
                 fence_proxy_async();
-                mbar_arrive(&sh.in_ready[s][part]);
+                mbar_arrive(&sh.in_ready[s]);
             }
             // -------------------------- op 7: views layer (64 = 2 x 32) ------------------------------------
             {
@@ -298,13 +329,15 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                 epilogue<32, false, true>(t_acc + part * 32, t_mod, slot + OFF_H0, row, part * 4);
                 tc_fence_before();
                 fence_proxy_async();
-                mbar_arrive(&sh.in_ready[s][part]);
+                mbar_arrive(&sh.in_ready[s]);
             }
             if (part == 1) { par_op8 = par_acc; par_acc ^= 1; pending_op8 = true; continue; }   // op 8 + compositing: part 0
             // -------------------------- op 8: rgb ----------------------------------------------------------
             float cr, cg, cb;
             {
+                TC_TRACE(48);
                 mbar_wait(&sh.acc_ready[s], par_acc); par_acc ^= 1;
+                TC_TRACE(49);
                 tc_fence_after();
                 uint32_t r16[16];
                 tmem_ld16(t_acc, r16);
@@ -315,176 +348,137 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                 cb = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(r16[2]) + br2)));
             }
             // -------------------------- compositing (renderer.py:18-26,65-92) ----------------------------------
+            // every row publishes (alpha, r, g, b); the first RT threads of the slot then walk their ray's
+            // SP samples of this tile front to back -- the reference's sequential cumprod order.
+            TC_TRACE(50);
             {
-                const float alpha = 1.f - __expf(-sigma);
-                const float fac = (1.f - alpha) + 1e-10f;
-                const int seg = S < 32 ? S : 32;                  // scan segment inside a warp
-                const int ls = lane & (seg - 1);
-                float incl = fac;
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const float u = __shfl_up_sync(0xffffffffu, incl, off);
-                    if (off < seg && ls >= off) incl *= u;
-                }
-                float T = __shfl_up_sync(0xffffffffu, incl, 1);
-                if (ls == 0) T = 1.f;
-                const int wpr = S >= 128 ? 4 : (S > 32 ? S / 32 : 1);   // warps per ray inside a tile
-                if (S > 32) {
-                    if (lane == 31) sh.scan[s][wq][0] = incl;
-                    named_bar_sync(1 + s, 128);
-                    const int w0 = wq - (wq % wpr);
-                    for (int w = w0; w < wq; ++w) T *= sh.scan[s][w][0];
-                    if (nchunks > 1 && chunk > 0) T *= sh.carry[s][0];
-                }
-                const float wgt = alpha * T;
-                if (valid) {
-                    if (io.alpha) io.alpha[si] = alpha;
-                    if (io.weights) io.weights[si] = wgt;
-                }
-                float v0 = wgt * cr, v1 = wgt * cg, v2 = wgt * cb, v3 = wgt * zv, v4 = wgt;
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    if (off < seg) {
-                        v0 += __shfl_xor_sync(0xffffffffu, v0, off); v1 += __shfl_xor_sync(0xffffffffu, v1, off);
-                        v2 += __shfl_xor_sync(0xffffffffu, v2, off); v3 += __shfl_xor_sync(0xffffffffu, v3, off);
-                        v4 += __shfl_xor_sync(0xffffffffu, v4, off);
-                    }
-                }
-                if (S > 32) {
-                    if (lane == 0) {
-                        sh.scan[s][wq][1] = v0; sh.scan[s][wq][2] = v1; sh.scan[s][wq][3] = v2;
-                        sh.scan[s][wq][4] = v3; sh.scan[s][wq][5] = v4;
-                    }
-                    named_bar_sync(1 + s, 128);
-                    if (lane == 0 && (wq % wpr) == 0) {
-                        for (int w = wq + 1; w < wq + wpr; ++w) {
-                            v0 += sh.scan[s][w][1]; v1 += sh.scan[s][w][2]; v2 += sh.scan[s][w][3];
-                            v3 += sh.scan[s][w][4]; v4 += sh.scan[s][w][5];
-                        }
-                        if (nchunks > 1) {
-                            float tall = sh.scan[s][0][0] * sh.scan[s][1][0] * sh.scan[s][2][0] * sh.scan[s][3][0];
-                            if (chunk > 0) {
-                                tall *= sh.carry[s][0];
-                                v0 += sh.carry[s][1]; v1 += sh.carry[s][2]; v2 += sh.carry[s][3];
-                                v3 += sh.carry[s][4]; v4 += sh.carry[s][5];
+                float4* xch = reinterpret_cast<float4*>(smem + XCH_OFFSET + s * 2048);
+                xch[row] = make_float4(1.f - __expf(-sigma), cr, cg, cb);
+                named_bar_sync(1 + s, 128);
+                TC_TRACE(51);
+                if (row < RT) {
+                    if (tile == 0) { cT = 1.f; c0 = c1 = c2 = c3 = c4 = 0.f; }
+                    const int cray = g * RT + row;
+                    if (cray < N) {
+                        float znear = 0.f, zfar = 0.f;
+                        if (FAST) { const float4 r1 = __ldg(reinterpret_cast<const float4*>(io.rays + (size_t)cray * 8) + 1); znear = r1.z; zfar = r1.w; }
+                        for (int sub = 0; sub < SP; ++sub) {
+                            const int sj = tile * SP + sub;
+                            if (sj >= S) break;
+                            const float4 v = xch[sub * RT + row];
+                            float z;
+                            if (FAST) {
+                                const float t = __ldg(io.t_steps + sj);
+                                if (!io.rg.lindisp) z = __fadd_rn(__fmul_rn(znear, 1.f - t), __fmul_rn(zfar, t));
+                                else z = __fdiv_rn(1.f, __fadd_rn(__fmul_rn(__fdiv_rn(1.f, znear), 1.f - t), __fmul_rn(__fdiv_rn(1.f, zfar), t)));
+                            } else {
+                                z = __ldg(io.z + (size_t)cray * S + sj);
                             }
-                            sh.carry[s][0] = tall; sh.carry[s][1] = v0; sh.carry[s][2] = v1; sh.carry[s][3] = v2;
-                            sh.carry[s][4] = v3; sh.carry[s][5] = v4;
+                            const float wgt = v.x * cT;
+                            if (io.alpha) io.alpha[(size_t)cray * S + sj] = v.x;
+                            if (io.weights) io.weights[(size_t)cray * S + sj] = wgt;
+                            c0 = fmaf(wgt, v.y, c0); c1 = fmaf(wgt, v.z, c1); c2 = fmaf(wgt, v.w, c2);
+                            c3 = fmaf(wgt, z, c3); c4 += wgt;
+                            cT *= (1.f - v.x) + 1e-10f;
+                        }
+                        if (tile == NT - 1) {
+                            float o0 = c0, o1 = c1, o2 = c2;
+                            if (sc.white_bkgd) { const float bg = 1.f - c4; o0 += bg; o1 += bg; o2 += bg; }
+                            io.rgb[(size_t)cray * 3 + 0] = o0; io.rgb[(size_t)cray * 3 + 1] = o1; io.rgb[(size_t)cray * 3 + 2] = o2;
+                            io.depth[cray] = c3;
                         }
                     }
-                    named_bar_sync(1 + s, 128);               // scratch + carry are stable before the next tile
                 }
-                const bool writer = S > 32 ? (lane == 0 && (wq % wpr) == 0) : (ls == 0);
-                if (writer && valid && chunk == nchunks - 1) {
-                    if (sc.white_bkgd) { const float bg = 1.f - v4; v0 += bg; v1 += bg; v2 += bg; }
-                    io.rgb[(size_t)ray * 3 + 0] = v0; io.rgb[(size_t)ray * 3 + 1] = v1; io.rgb[(size_t)ray * 3 + 2] = v2;
-                    io.depth[ray] = v3;
-                }
+                TC_TRACE(53);
             }
         }
     } else if (warp == 16) {
         // =========================== MMA issuer ========================================================
-        if (lane == 0) {
+        // the whole warp walks the schedule (waits are warp-uniform); one elected lane issues
+        const bool leader = elect_one();
+        {
             uint32_t par_in[2] = {0, 0};
             const uint32_t sbase = smem_u32(smem);
             const uint32_t ring = sbase + RING_OFFSET;
-            constexpr uint32_t ID128 = idesc_f16(128, 128), ID144 = idesc_f16(128, 144),
-                               ID64 = idesc_f16(128, 64), ID16 = idesc_f16(128, 16);
             // descriptors: hi word constant per layout, lo word = (addr >> 4) | LBO field; a K-step adds 32 B = 2 units
             constexpr uint32_t HI_SW = (uint32_t)(desc_sw128(0) >> 32), HI_NS = (uint32_t)(desc_nosw(0, 128, 256) >> 32);
             constexpr uint32_t LO_SW = (uint32_t)desc_sw128(0), LO_NS = (uint32_t)desc_nosw(0, 128, 256);
             auto dsw = [&](uint32_t addr) { return ((uint64_t)HI_SW << 32) | (uint64_t)(LO_SW | (addr >> 4)); };
             auto dns = [&](uint32_t addr) { return ((uint64_t)HI_NS << 32) | (uint64_t)(LO_NS | (addr >> 4)); };
             uint32_t nchunk_base = 0;                         // global chunk counter at the start of the pass
+#pragma unroll 1
             for (int pass = 0; pass < npass; ++pass) {
                 const bool act[2] = {group_of(pass, 0) < G, group_of(pass, 1) < G};
-                auto stage_addr = [&](int c) { return ring + ((nchunk_base + c) % tcw::NSTAGE) * tcw::STAGE_BYTES; };
-                auto wait_full = [&](int c) {
-                    const uint32_t n = nchunk_base + c;
-                    mbar_wait(&sh.w_full[n % tcw::NSTAGE], (n / tcw::NSTAGE) & 1);
-                };
-                auto release = [&](int c) { mma_commit(&sh.w_empty[(nchunk_base + c) % tcw::NSTAGE]); };
-                // NSTEPS K-steps (16 columns each) over one swizzled K-block
-                auto block2 = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t accum) {
-                    const uint64_t da = dsw(a), db = dsw(b);
-                    mma_f16(d, da, db, idesc, accum);
-                    mma_f16(d, da + 2, db + 2, idesc, 1);
-                };
-                auto block4 = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t idesc, uint32_t accum) {
-                    const uint64_t da = dsw(a), db = dsw(b);
-                    mma_f16(d, da, db, idesc, accum);
-                    mma_f16(d, da + 2, db + 2, idesc, 1);
-                    mma_f16(d, da + 4, db + 4, idesc, 1);
-                    mma_f16(d, da + 6, db + 6, idesc, 1);
-                };
+                // one generic body per (op, slot), driven by the op tables (kept small on purpose: this code
+                // runs once per pass and must not evict the epilogue loop from the instruction cache)
+#pragma unroll 1
                 for (int op = 0; op < 9; ++op) {
+                    const int nblk = c_op_nblk[op];
+                    const uint32_t idesc = c_op_idesc[op];
+#pragma unroll 1
                     for (int s = 0; s < 2; ++s) {
                         if (!act[s]) continue;
                         const bool first = (s == 0) || !act[0], last = (s == 1) || !act[1];
-                        mbar_wait(&sh.in_ready[s][0], par_in[s]); mbar_wait(&sh.in_ready[s][1], par_in[s]); par_in[s] ^= 1;
-                        const uint32_t sl = sbase + s * SLOT_BYTES;
-                        const uint32_t d_acc = tmem + s * 256, d_mod = d_acc + 128;
-                        if (op == 0) {
-                            if (first) { wait_full(0); wait_full(1); }
-                            tc_fence_after();
-                            block2(d_mod, sl + OFF_MISC, stage_addr(0), ID128, 0);               // modulation (K = 20 + 1)
-                            block4(d_acc, sl + OFF_PE, stage_addr(1), ID128, 0);                 // layer 0    (K = 63 + 1)
-                            mma_commit(&sh.acc_ready[s]);
-                            if (last) { release(0); release(1); }
-                        } else if (op <= 4) {                                                    // layers 1..4
-                            const int c = 2 * op;
-                            if (first) { wait_full(c); wait_full(c + 1); }
-                            tc_fence_after();
-                            block4(d_acc, sl + OFF_H0, stage_addr(c), ID128, 0);
-                            block4(d_acc, sl + OFF_H1, stage_addr(c + 1), ID128, 1);
-                            mma_f16(d_acc, dsw(sl + OFF_MISC + 32), dns(stage_addr(c + 1) + 16384), ID128, 1);   // bias step
-                            mma_commit(&sh.acc_ready[s]);
-                            if (last) { release(c); release(c + 1); }
-                        } else if (op == 5) {                                                    // layer 5: [pe | h]
-                            if (first) { wait_full(10); wait_full(11); wait_full(12); }
-                            tc_fence_after();
-                            block4(d_acc, sl + OFF_PE, stage_addr(10), ID128, 0);
-                            block4(d_acc, sl + OFF_H0, stage_addr(11), ID128, 1);
-                            block4(d_acc, sl + OFF_H1, stage_addr(12), ID128, 1);
-                            mma_commit(&sh.acc_ready[s]);
-                            if (last) { release(10); release(11); release(12); }
-                        } else if (op == 6) {                                                    // feature (128) + sigma (col 128)
-                            if (first) { wait_full(13); wait_full(14); }
-                            tc_fence_after();
-                            block4(d_acc, sl + OFF_H0, stage_addr(13), ID144, 0);
-                            block4(d_acc, sl + OFF_H1, stage_addr(14), ID144, 1);
-                            mma_f16(d_acc, dsw(sl + OFF_MISC + 32), dns(stage_addr(14) + 18432), ID144, 1);
-                            mma_commit(&sh.acc_ready[s]);
-                            if (last) { release(13); release(14); }
-                        } else if (op == 7) {                                                    // views: [feature | dir]
-                            if (first) { wait_full(15); wait_full(16); }
-                            tc_fence_after();
-                            block4(d_acc, sl + OFF_H0, stage_addr(15), ID64, 0);
-                            block4(d_acc, sl + OFF_H1, stage_addr(16), ID64, 1);
-                            mma_f16(d_acc, dsw(sl + OFF_MISC + 64), dns(stage_addr(16) + 8192), ID64, 1);
-                            mma_commit(&sh.acc_ready[s]);
-                            if (last) { release(15); release(16); }
-                        } else {                                                                 // rgb (N = 16, 3 used)
-                            if (first) wait_full(17);
-                            tc_fence_after();
-                            block4(d_acc, sl + OFF_H0, stage_addr(17), ID16, 0);
-                            mma_commit(&sh.acc_ready[s]);
-                            if (last) release(17);
+                        if (first) {                                      // weights first: they normally landed long ago
+#pragma unroll 1
+                            for (int b = 0; b < nblk; ++b) {
+                                const uint32_t n = nchunk_base + c_blk_chunk[op][b];
+                                mbar_wait(&sh.w_full[n % tcw::NSTAGE], (n / tcw::NSTAGE) & 1);
+                            }
                         }
+                        TC_TRACE(100 + op * 2 + s);
+                        mbar_wait(&sh.in_ready[s], par_in[s]); par_in[s] ^= 1;
+                        TC_TRACE(140 + op * 2 + s);
+                        tc_fence_after();
+                        const uint32_t sl = sbase + s * SLOT_BYTES;
+                        const uint32_t d_acc = tmem + s * 256;
+                        TC_TRACE(60 + op * 2 + s);
+                        if (leader) {
+                            uint32_t last_stage = 0;
+#pragma unroll 1
+                            for (int b = 0; b < nblk; ++b) {
+                                const uint32_t st = ring + ((nchunk_base + c_blk_chunk[op][b]) % tcw::NSTAGE) * tcw::STAGE_BYTES;
+                                last_stage = st;
+                                const bool to_mod = (op == 0 && b == 0);          // modulation GEMM: K = 32, own TMEM columns
+                                const uint32_t d = to_mod ? d_acc + 128 : d_acc;
+                                const uint64_t da = dsw(sl + c_blk_aoff[op][b]), db = dsw(st);
+                                const uint32_t acc0 = (b > 0 && op != 0) ? 1u : 0u;
+                                mma_f16(d, da, db, idesc, acc0);
+                                mma_f16(d, da + 2, db + 2, idesc, 1);
+                                if (!to_mod) {
+                                    mma_f16(d, da + 4, db + 4, idesc, 1);
+                                    mma_f16(d, da + 6, db + 6, idesc, 1);
+                                }
+                            }
+                            if (c_op_bias_aoff[op])                               // constant-one column x bias row ("bias step")
+                                mma_f16(d_acc, dsw(sl + c_op_bias_aoff[op]), dns(last_stage + c_op_bias_boff[op]), idesc, 1);
+                            TC_TRACE(80 + op * 2 + s);
+                            mma_commit(&sh.acc_ready[s]);
+                            if (last) mma_commit(&sh.w_free);             // this op's chunks are free once these MMAs retire
+                        }
+                        __syncwarp();
                     }
                 }
+                TC_TRACE(200);
                 nchunk_base += tcw::NCHUNK;
             }
         }
     } else {
         // =========================== weight loader ========================================================
-        if (lane == 0) {
+        if (elect_one()) {
             uint8_t* ring = smem + RING_OFFSET;
-            uint32_t n = 0;
+            uint32_t n = 0, ops_freed = 0;                  // chunks issued, w_free phases consumed
+#pragma unroll 1
             for (int pass = 0; pass < npass; ++pass) {
+#pragma unroll 1
                 for (int c = 0; c < tcw::NCHUNK; ++c, ++n) {
                     const uint32_t st = n % tcw::NSTAGE;
-                    mbar_wait(&sh.w_empty[st], ((n / tcw::NSTAGE) & 1) ^ 1);
+                    if (n >= (uint32_t)tcw::NSTAGE) {
+                        // the stage's previous tenant is chunk n - NSTAGE; wait until its op has been released
+                        const uint32_t pn = n - tcw::NSTAGE;
+                        const uint32_t need = (pn / tcw::NCHUNK) * 9 + (uint32_t)c_chunk_op[pn % tcw::NCHUNK];
+                        while (ops_freed <= need) { mbar_wait(&sh.w_free, ops_freed & 1); ++ops_freed; }
+                    }
                     const uint32_t bytes = (uint32_t)tcw::chunk_bytes(c);
                     mbar_arrive_expect_tx(&sh.w_full[st], bytes);
                     bulk_load(ring + st * tcw::STAGE_BYTES, wimg + tcw::chunk_offset(c), bytes, &sh.w_full[st]);
@@ -497,14 +491,15 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
     if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
-int launch_render_tc(const SceneDev& sc, const RenderIO& io, bool fast, const void* wimg, cudaStream_t stream) {
-    const int S = io.S;
-    MVSN_REQUIRE((S <= 128 && 128 % S == 0) || (S > 128 && S % 128 == 0), MVSN_EUNSUPPORTED,
-                 "tensor-core render mode needs N_samples dividing 128 or a multiple of 128 (got %d); use MVSN_MLP_FP32", S);
+int launch_render_tc(const SceneDev& sc, const RenderIO& io_in, bool fast, const void* wimg, cudaStream_t stream) {
+    RenderIO io = io_in;
     MVSN_CUDA_CHECK(cudaFuncSetAttribute(render_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     MVSN_CUDA_CHECK(cudaFuncSetAttribute(render_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    const int R = S <= 128 ? 128 / S : 1;
-    const int G = (io.N + R - 1) / R;
+    // rays per tile: 32 (best gather locality) unless the batch is too small to give every SM a pair of groups
+    int rt = 32;
+    while (rt > 4 && (io.N + rt - 1) / rt < 2 * sm_count()) rt >>= 1;
+    io.rays_per_tile = rt;
+    const int G = (io.N + rt - 1) / rt;
     const int pairs = (G + 1) / 2;
     const int grid = pairs < sm_count() ? pairs : sm_count();
     if (grid <= 0) return MVSN_OK;

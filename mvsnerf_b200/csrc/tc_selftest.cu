@@ -11,7 +11,7 @@ using namespace umma;
 
 __global__ void __launch_bounds__(128, 1)
 umma_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B, const __half* __restrict__ Bc,
-                     int N, int K, float* __restrict__ D) {
+                     int N, int K, float* __restrict__ D, int reps, long long* __restrict__ cycles) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // SWIZZLE_128B tiles: 1024-B aligned
     const int nkb = K / 64;
@@ -42,7 +42,7 @@ umma_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
     }
     fence_proxy_async();
     if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
-    if (warp == 0) { tmem_alloc(&tmem_base_holder, 256); tmem_relinquish(); }
+    if (warp == 0) { tmem_alloc(&tmem_base_holder, 512); tmem_relinquish(); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -60,7 +60,16 @@ umma_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
         }
         if (Bc)   // D += A[:, 16:32] * Bc^T : A chunk from the swizzled block, B chunk from the no-swizzle tile
             mma_f16(tmem, desc_sw128(smem_u32(sA) + 32), desc_nosw(smem_u32(sBc), 128, 256), idesc, 1);
+        long long t0 = clock64();
+        for (int r = 0; r < reps; ++r) {                     // throughput probe: re-issue the K-steps into other columns
+            for (int kb = 0; kb < nkb; ++kb) {
+                const uint32_t a0 = smem_u32(sA + kb * 128 * 128), b0 = smem_u32(sB + kb * N * 128);
+                for (int ks = 0; ks < 4; ++ks)
+                    mma_f16(tmem + 256, desc_sw128(a0 + ks * 32), desc_sw128(b0 + ks * 32), idesc, 1);
+            }
+        }
         mma_commit(&bar);
+        if (reps > 0) { mbar_wait(&bar, 0); cycles[0] = clock64() - t0; }
     }
     mbar_wait(&bar, 0);
     tc_fence_after();
@@ -74,12 +83,21 @@ umma_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace mvsn
 
 using namespace mvsn;
+
+extern "C" int mvsn_selftest_umma_probe(const void* A, const void* B, int N, int K, float* D, int reps, long long* cycles, void* stream) {
+    const size_t smem = (size_t)(K / 64) * (128 + N) * 128 + (size_t)N * 32 + 1024;
+    MVSN_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(
+        static_cast<const __half*>(A), static_cast<const __half*>(B), nullptr, N, K, D, reps, cycles);
+    MVSN_CUDA_CHECK(cudaGetLastError());
+    return MVSN_OK;
+}
 
 extern "C" int mvsn_selftest_umma(const void* A, const void* B, const void* Bc, int N, int K, float* D, void* stream) {
     MVSN_REQUIRE(A && B && D, MVSN_ENULL, "mvsn_selftest_umma: NULL argument");
@@ -88,7 +106,7 @@ extern "C" int mvsn_selftest_umma(const void* A, const void* B, const void* Bc, 
     const size_t smem = (size_t)(K / 64) * (128 + N) * 128 + (size_t)N * 32 + 1024;
     MVSN_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(
-        static_cast<const __half*>(A), static_cast<const __half*>(B), static_cast<const __half*>(Bc), N, K, D);
+        static_cast<const __half*>(A), static_cast<const __half*>(B), static_cast<const __half*>(Bc), N, K, D, 0, nullptr);
     MVSN_CUDA_CHECK(cudaGetLastError());
     return MVSN_OK;
 }

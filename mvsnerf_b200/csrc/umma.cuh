@@ -10,6 +10,18 @@ namespace umma {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a fully converged warp (the tensor / bulk-copy instructions below are issued by it)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier ------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");

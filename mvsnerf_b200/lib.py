@@ -22,7 +22,7 @@ EXPORTS = [
     "mvsn_pack_images", "mvsn_volume_to_channels_last", "mvsn_volume_from_channels_last",
     "mvsn_render_samples", "mvsn_render_rays", "mvsn_cost_volume_workspace_bytes",
     "mvsn_build_cost_volume", "mvsn_costreg_workspace_bytes", "mvsn_costreg_forward",
-    "mvsn_selftest_umma",
+    "mvsn_selftest_umma", "mvsn_debug_set_trace",
 ]
 
 
@@ -67,6 +67,8 @@ def load() -> C.CDLL:
     lib.mvsn_costreg_workspace_bytes.restype = C.c_size_t
     lib.mvsn_costreg_workspace_bytes.argtypes = [ip, ip, ip]
     lib.mvsn_costreg_forward.argtypes = [C.POINTER(vp), vp, ip, ip, ip, vp, vp, C.c_size_t, vp]
+    lib.mvsn_debug_set_trace.argtypes = [vp]
+    lib.mvsn_debug_set_trace.restype = None
     lib.mvsn_selftest_umma.argtypes = [vp, vp, vp, ip, ip, vp, vp]
     for name in ("mvsn_selftest_umma", "mvsn_mlp_pack", "mvsn_pack_images", "mvsn_volume_to_channels_last",
                  "mvsn_volume_from_channels_last", "mvsn_render_samples", "mvsn_render_rays",
