@@ -73,26 +73,36 @@ __device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
                  :: "memory");
 }
 
-// 16 accumulator columns -> (x mod) -> relu -> fp16 -> two 16-byte chunks of an operand K-block
+// two fp32 -> packed fp16x2 (low half = first argument), optionally clamped at zero by the converter
+template <bool RELU>
+__device__ __forceinline__ uint32_t cvt_h2(float lo, float hi) {
+    uint32_t r;
+    if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    else      asm("cvt.rn.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+// 16 accumulator columns -> (x mod) -> relu -> fp16 -> two 16-byte chunks of an operand K-block.
+// `rowaddr` = shared address of the row inside the (1024-aligned) K-block with the row's swizzle
+// phase already folded in, so chunk kc lives at rowaddr ^ (kc * 16).
 template <bool MODULATE, bool RELU>
-__device__ __forceinline__ void emit16(const uint32_t (&a)[16], const uint32_t (&m)[16], uint8_t* blk, int row, int kc) {
+__device__ __forceinline__ void emit16(const uint32_t (&a)[16], const uint32_t (&m)[16], uint32_t rowaddr, int kc) {
     uint32_t p[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         float2 x = make_float2(__uint_as_float(a[2 * j]), __uint_as_float(a[2 * j + 1]));
         if (MODULATE) x = __fmul2_rn(x, make_float2(__uint_as_float(m[2 * j]), __uint_as_float(m[2 * j + 1])));
-        __half2 h = __floats2half2_rn(x.x, x.y);
-        if (RELU) h = __hmax2(h, __float2half2_rn(0.f));
-        p[j] = *reinterpret_cast<uint32_t*>(&h);
+        p[j] = cvt_h2<RELU>(x.x, x.y);
     }
-    *reinterpret_cast<uint4*>(blk + sw128_offset(row, kc * 8)) = make_uint4(p[0], p[1], p[2], p[3]);
-    *reinterpret_cast<uint4*>(blk + sw128_offset(row, kc * 8 + 8)) = make_uint4(p[4], p[5], p[6], p[7]);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(rowaddr ^ (uint32_t)(kc * 16)), "r"(p[0]), "r"(p[1]), "r"(p[2]), "r"(p[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(rowaddr ^ (uint32_t)((kc + 1) * 16)), "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7]) : "memory");
 }
 
 // epilogue over NCOL (multiple of 16) accumulator columns starting at t_acc / t_mod, written to
 // K-block `blk` starting at 16-byte chunk kc0; TMEM loads of chunk i+1 fly while chunk i is processed
 template <int NCOL, bool MODULATE, bool RELU>
 __device__ __forceinline__ void epilogue(uint32_t t_acc, uint32_t t_mod, uint8_t* blk, int row, int kc0) {
+    const uint32_t rowaddr = smem_u32(blk) + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + (row & 7) * 16);
     uint32_t a[2][16], m[2][16];
     tmem_ld16(t_acc, a[0]);
     if (MODULATE) tmem_ld16(t_mod, m[0]);
@@ -104,7 +114,7 @@ __device__ __forceinline__ void epilogue(uint32_t t_acc, uint32_t t_mod, uint8_t
             tmem_ld16(t_acc + (i + 1) * 16, a[(i + 1) & 1]);
             if (MODULATE) tmem_ld16(t_mod + (i + 1) * 16, m[(i + 1) & 1]);
         }
-        emit16<MODULATE, RELU>(a[i & 1], m[i & 1], blk, row, kc0 + 2 * i);
+        emit16<MODULATE, RELU>(a[i & 1], m[i & 1], rowaddr, kc0 + 2 * i);
     }
 }
 
