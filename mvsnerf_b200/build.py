@@ -43,17 +43,22 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    os.makedirs(BUILD_DIR, exist_ok=True)
-    stamp = os.path.join(BUILD_DIR, "stamp")
-    digest = _digest()
-    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == digest:
-        return LIB_PATH
+def build_library(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """trace=True builds libmvsnerf_b200_trace.so with the pipeline-timeline hooks compiled in
+    (tools/tc_trace.py loads it through MVSN_LIB); the product library never carries them."""
+    build_dir = BUILD_DIR + ("_trace" if trace else "")
+    lib_path = LIB_PATH.replace(".so", "_trace.so") if trace else LIB_PATH
+    flags = NVCC_FLAGS + (["-DMVSN_TC_TRACE"] if trace else [])
+    os.makedirs(build_dir, exist_ok=True)
+    stamp = os.path.join(build_dir, "stamp")
+    digest = _digest() + ("trace" if trace else "")
+    if not force and os.path.exists(lib_path) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return lib_path
     nvcc = _nvcc()
 
     def compile_one(src):
-        obj = os.path.join(BUILD_DIR, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        obj = os.path.join(build_dir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc, *flags, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(obj + ".log", "w") as f:
@@ -66,15 +71,15 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, _sources()))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs]
+    cmd = [nvcc, "-shared", "-o", lib_path, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     with open(stamp, "w") as f:
         f.write(digest)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build_library(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    path = build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv)
     print(path)

@@ -53,7 +53,8 @@ struct TcShared {
     uint64_t in_ready[2];       // slot group (256 arrivals) -> MMA issuer: operand tile written
     uint64_t acc_ready[2];      // tcgen05.commit -> slot group: accumulator complete
     uint64_t w_full[tcw::NSTAGE];
-    uint64_t w_free;            // one phase per GEMM op: its weight chunks may be overwritten
+    uint64_t w_free[4];         // GEMM op k (global index) signals w_free[k & 3] when its weight chunks may be overwritten;
+                                // four barriers in rotation keep a late waiter at most one phase behind (no parity aliasing)
     uint32_t tmem_base;
     Cams cams;
 };
@@ -154,7 +155,7 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
             mbar_init(&sh.acc_ready[s], 1);
         }
         for (int i = 0; i < tcw::NSTAGE; ++i) mbar_init(&sh.w_full[i], 1);
-        mbar_init(&sh.w_free, 1);
+        for (int i = 0; i < 4; ++i) mbar_init(&sh.w_free[i], 1);
         fence_barrier_init();
     }
     if (warp == 16) { tmem_alloc(&sh.tmem_base, 512); tmem_relinquish(); }
@@ -192,215 +193,230 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
         uint8_t* slot = smem + s * SLOT_BYTES;
         const uint32_t t_acc = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(s * 256);
         const uint32_t t_mod = t_acc + 128;
-        uint32_t par_acc = 0, par_op8 = 0;
+        uint32_t par_acc = 0;
         float cT = 1.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f;   // compositing state of ray `row` (row < RT)
-        bool pending_op8 = false;                            // part 1 skips the op-8 wait; it is made up before the next arrive
+
         const float br0 = __ldg(reinterpret_cast<const float*>(wimg + tcw::TAIL_OFFSET));
         const float br1 = __ldg(reinterpret_cast<const float*>(wimg + tcw::TAIL_OFFSET) + 1);
         const float br2 = __ldg(reinterpret_cast<const float*>(wimg + tcw::TAIL_OFFSET) + 2);
         uint8_t* hblk = slot + (part ? OFF_H1 : OFF_H0);
 
-        for (int pass = 0; pass < npass; ++pass) {
-            const int g = group_of(pass, s), tile = pass % NT;
-            if (g >= G) continue;                            // this slot idles in the last pass
-            TC_TRACE(1);
-            // -------------------------- front end -------------------------------------------------
-            const int r_in = row & (RT - 1), s_idx = tile * SP + (row >> rt_shift);
-            const int ray = g * RT + r_in;
-            const bool valid = ray < N && s_idx < S;
-            const size_t si = (size_t)ray * S + s_idx;
-            float nx = 0.f, ny = 0.f, nz = 0.f, zv = 0.f;
-            float px = 0.f, py = 0.f, pz = 0.f, dx = 0.f, dy = 0.f, dz = 1.f;
-            if (valid) {
-                if (FAST) {
-                    const float4* rp = reinterpret_cast<const float4*>(io.rays + (size_t)ray * 8);
-                    float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-                    dx = r0.w; dy = r1.x; dz = r1.y;
-                    const float near = r1.z, far = r1.w, t = __ldg(io.t_steps + s_idx);
-                    if (!io.rg.lindisp) zv = __fadd_rn(__fmul_rn(near, 1.f - t), __fmul_rn(far, t));
-                    else zv = __fdiv_rn(1.f, __fadd_rn(__fmul_rn(__fdiv_rn(1.f, near), 1.f - t),
-                                                       __fmul_rn(__fdiv_rn(1.f, far), t)));
-                    px = __fadd_rn(r0.x, __fmul_rn(dx, zv));
-                    py = __fadd_rn(r0.y, __fmul_rn(dy, zv));
-                    pz = __fadd_rn(r0.z, __fmul_rn(dz, zv));
-                    ndc_of_point<false>(sc, sh.cams, io.rg, px, py, pz, nx, ny, nz);
-                } else {
-                    px = __ldg(io.pts + si * 3); py = __ldg(io.pts + si * 3 + 1); pz = __ldg(io.pts + si * 3 + 2);
-                    nx = __ldg(io.ndc + si * 3); ny = __ldg(io.ndc + si * 3 + 1); nz = __ldg(io.ndc + si * 3 + 2);
-                    zv = __ldg(io.z + si);
-                    dx = __ldg(io.dirs + (size_t)ray * 3); dy = __ldg(io.dirs + (size_t)ray * 3 + 1);
-                    dz = __ldg(io.dirs + (size_t)ray * 3 + 2);
+        // The loop is rotated by one tile: between the views-layer epilogue (op 7) and the rgb result (op 8) of
+        // the tile in flight, every thread already builds its share of the NEXT tile's operand tiles (PE / MISC
+        // are last read by ops 5 / 7), so the front end hides under the rgb GEMM and the compositing.
+        float sigma = 0.f;
+        int g_cur = 0, tile_cur = 0;
+        bool act_cur = false;
+        for (int pass = -1; pass < npass; ++pass) {
+            if (act_cur) {
+                // -------------------------- trunk: ops 0..5 -> h ------------------------------------------
+    #pragma unroll 1
+                for (int op = 0; op < 6; ++op) {
+                    mbar_wait(&sh.acc_ready[s], par_acc); par_acc ^= 1;
+                    TC_TRACE(10 + op);
+                    tc_fence_after();
+                    epilogue<64, true, true>(t_acc + part * 64, t_mod + part * 64, hblk, row, 0);
+                    tc_fence_before();
+                    fence_proxy_async();
+                    TC_TRACE(30 + op);
+                    mbar_arrive(&sh.in_ready[s]);
+                }
+                // -------------------------- op 6: feature (128) + sigma (col 128) ---------------------------
+                sigma = 0.f;
+                {
+                    mbar_wait(&sh.acc_ready[s], par_acc); par_acc ^= 1;
+                    tc_fence_after();
+                    epilogue<64, false, false>(t_acc + part * 64, t_mod, hblk, row, 0);
+                    if (part == 0) {
+                        uint32_t r16[16];
+                        tmem_ld16(t_acc + 128, r16);
+                        tmem_wait16(r16);
+                        sigma = fmaxf(__uint_as_float(r16[0]), 0.f);
+                    }
+                    tc_fence_before();
+                    fence_proxy_async();
+                    mbar_arrive(&sh.in_ready[s]);
+                }
+                // -------------------------- op 7: views layer (64 = 2 x 32) ------------------------------------
+                {
+                    mbar_wait(&sh.acc_ready[s], par_acc); par_acc ^= 1;
+                    tc_fence_after();
+                    epilogue<32, false, true>(t_acc + part * 32, t_mod, slot + OFF_H0, row, part * 4);
+                    tc_fence_before();
+                    fence_proxy_async();
+                    mbar_arrive(&sh.in_ready[s]);
                 }
             }
-            const float nd[3] = {nx, ny, nz};
-            TC_TRACE(3);
-            if (part == 0) {
-                // PE cols 0..31 = [x y z | sin(2^k x) for the first 29 of 30].  (part 0 also owns the rgb
-                // epilogue + compositing of the previous tile, so it gets the light half of the front end)
-                float v[32];
-                v[0] = nx; v[1] = ny; v[2] = nz;
-                float f = 1.f;
-#pragma unroll
-                for (int k = 0; k < 10; ++k) {
-#pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        if (3 + 3 * k + j < 32) v[3 + 3 * k + j] = __sinf(nd[j] * f);
-                    f *= 2.f;
-                }
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    *reinterpret_cast<uint4*>(slot + OFF_PE + sw128_offset(row, c * 8)) =
-                        make_uint4(pack_h2(v[c * 8], v[c * 8 + 1]), pack_h2(v[c * 8 + 2], v[c * 8 + 3]),
-                                   pack_h2(v[c * 8 + 4], v[c * 8 + 5]), pack_h2(v[c * 8 + 6], v[c * 8 + 7]));
-            } else {
-                // all gathers: volume (8) + colour (12) features + view direction -> MISC cols 0..47 ;
-                // PE cols 32..63 = [sin(512 z) | cos | 1].  This half starts while part 0 is still compositing.
-                float feat[20], dir[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-                for (int i = 0; i < 20; ++i) feat[i] = 0.f;
+            const int np = pass + 1;
+            const int g = np < npass ? group_of(np, s) : G, tile = np < npass ? np % NT : 0;
+            const bool act_next = g < G;                     // a slot only idles in the final passes
+            if (act_next) {
+                TC_TRACE(1);
+                // -------------------------- front end -------------------------------------------------
+                const int r_in = row & (RT - 1), s_idx = tile * SP + (row >> rt_shift);
+                const int ray = g * RT + r_in;
+                const bool valid = ray < N && s_idx < S;
+                const size_t si = (size_t)ray * S + s_idx;
+                float nx = 0.f, ny = 0.f, nz = 0.f, zv = 0.f;
+                float px = 0.f, py = 0.f, pz = 0.f, dx = 0.f, dy = 0.f, dz = 1.f;
                 if (valid) {
-                    view_dir<false>(sh.cams, dx, dy, dz, dir);
-                    sample_volume(sc, nx, ny, nz, feat);
-#pragma unroll
-                    for (int v = 0; v < 3; ++v) sample_color<false>(sc, sh.cams, v, px, py, pz, feat + 8 + 4 * v);
-                    if (io.input_feat) {
-                        float4* o = reinterpret_cast<float4*>(io.input_feat + si * 20);
-#pragma unroll
-                        for (int i = 0; i < 5; ++i)
-                            o[i] = make_float4(feat[4 * i], feat[4 * i + 1], feat[4 * i + 2], feat[4 * i + 3]);
+                    if (FAST) {
+                        const float4* rp = reinterpret_cast<const float4*>(io.rays + (size_t)ray * 8);
+                        float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                        dx = r0.w; dy = r1.x; dz = r1.y;
+                        const float near = r1.z, far = r1.w, t = __ldg(io.t_steps + s_idx);
+                        if (!io.rg.lindisp) zv = __fadd_rn(__fmul_rn(near, 1.f - t), __fmul_rn(far, t));
+                        else zv = __fdiv_rn(1.f, __fadd_rn(__fmul_rn(__fdiv_rn(1.f, near), 1.f - t),
+                                                           __fmul_rn(__fdiv_rn(1.f, far), t)));
+                        px = __fadd_rn(r0.x, __fmul_rn(dx, zv));
+                        py = __fadd_rn(r0.y, __fmul_rn(dy, zv));
+                        pz = __fadd_rn(r0.z, __fmul_rn(dz, zv));
+                        ndc_of_point<false>(sc, sh.cams, io.rg, px, py, pz, nx, ny, nz);
+                    } else {
+                        px = __ldg(io.pts + si * 3); py = __ldg(io.pts + si * 3 + 1); pz = __ldg(io.pts + si * 3 + 2);
+                        nx = __ldg(io.ndc + si * 3); ny = __ldg(io.ndc + si * 3 + 1); nz = __ldg(io.ndc + si * 3 + 2);
+                        zv = __ldg(io.z + si);
+                        dx = __ldg(io.dirs + (size_t)ray * 3); dy = __ldg(io.dirs + (size_t)ray * 3 + 1);
+                        dz = __ldg(io.dirs + (size_t)ray * 3 + 2);
                     }
                 }
-                TC_TRACE(4);
-                uint8_t* m = slot + OFF_MISC;
-                *reinterpret_cast<uint4*>(m + sw128_offset(row, 0)) =
-                    make_uint4(pack_h2(feat[0], feat[1]), pack_h2(feat[2], feat[3]), pack_h2(feat[4], feat[5]), pack_h2(feat[6], feat[7]));
-                *reinterpret_cast<uint4*>(m + sw128_offset(row, 8)) =
-                    make_uint4(pack_h2(feat[8], feat[9]), pack_h2(feat[10], feat[11]), pack_h2(feat[12], feat[13]), pack_h2(feat[14], feat[15]));
-                *reinterpret_cast<uint4*>(m + sw128_offset(row, 16)) =
-                    make_uint4(pack_h2(feat[16], feat[17]), pack_h2(feat[18], feat[19]), pack_h2(1.f, 0.f), 0u);
-                *reinterpret_cast<uint4*>(m + sw128_offset(row, 24)) = make_uint4(0u, 0u, 0u, 0u);
-                *reinterpret_cast<uint4*>(m + sw128_offset(row, 32)) =
-                    make_uint4(pack_h2(dir[0], dir[1]), pack_h2(dir[2], 1.f), 0u, 0u);
-                *reinterpret_cast<uint4*>(m + sw128_offset(row, 40)) = make_uint4(0u, 0u, 0u, 0u);
-                TC_TRACE(5);
-                float v[32];
-                v[0] = __sinf(nz * 512.f);
-                float f = 1.f;
-#pragma unroll
-                for (int k = 0; k < 10; ++k) {
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) v[1 + 3 * k + j] = __cosf(nd[j] * f);
-                    f *= 2.f;
-                }
-                v[31] = 1.f;
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    *reinterpret_cast<uint4*>(slot + OFF_PE + sw128_offset(row, 32 + c * 8)) =
-                        make_uint4(pack_h2(v[c * 8], v[c * 8 + 1]), pack_h2(v[c * 8 + 2], v[c * 8 + 3]),
-                                   pack_h2(v[c * 8 + 4], v[c * 8 + 5]), pack_h2(v[c * 8 + 6], v[c * 8 + 7]));
-            }
-            fence_proxy_async();
-            TC_TRACE(2);
-            if (pending_op8) { mbar_wait(&sh.acc_ready[s], par_op8); pending_op8 = false; }   // previous tile's op 8 retired
-            mbar_arrive(&sh.in_ready[s]);
-
-            // -------------------------- trunk: ops 0..5 -> h ------------------------------------------
-#pragma unroll 1
-            for (int op = 0; op < 6; ++op) {
-                mbar_wait(&sh.acc_ready[s], par_acc); par_acc ^= 1;
-                TC_TRACE(10 + op);
-                tc_fence_after();
-                epilogue<64, true, true>(t_acc + part * 64, t_mod + part * 64, hblk, row, 0);
-                tc_fence_before();
-                fence_proxy_async();
-                TC_TRACE(30 + op);
-                mbar_arrive(&sh.in_ready[s]);
-            }
-            // -------------------------- op 6: feature (128) + sigma (col 128) ---------------------------
-            float sigma = 0.f;
-            {
-                mbar_wait(&sh.acc_ready[s], par_acc); par_acc ^= 1;
-                tc_fence_after();
-                epilogue<64, false, false>(t_acc + part * 64, t_mod, hblk, row, 0);
+                const float nd[3] = {nx, ny, nz};
+                TC_TRACE(3);
                 if (part == 0) {
-                    uint32_t r16[16];
-                    tmem_ld16(t_acc + 128, r16);
-                    tmem_wait16(r16);
-                    sigma = fmaxf(__uint_as_float(r16[0]), 0.f);
-                }
-                tc_fence_before();
-                fence_proxy_async();
-                mbar_arrive(&sh.in_ready[s]);
-            }
-            // -------------------------- op 7: views layer (64 = 2 x 32) ------------------------------------
-            {
-                mbar_wait(&sh.acc_ready[s], par_acc); par_acc ^= 1;
-                tc_fence_after();
-                epilogue<32, false, true>(t_acc + part * 32, t_mod, slot + OFF_H0, row, part * 4);
-                tc_fence_before();
-                fence_proxy_async();
-                mbar_arrive(&sh.in_ready[s]);
-            }
-            if (part == 1) { par_op8 = par_acc; par_acc ^= 1; pending_op8 = true; continue; }   // op 8 + compositing: part 0
-            // -------------------------- op 8: rgb ----------------------------------------------------------
-            float cr, cg, cb;
-            {
-                TC_TRACE(48);
-                mbar_wait(&sh.acc_ready[s], par_acc); par_acc ^= 1;
-                TC_TRACE(49);
-                tc_fence_after();
-                uint32_t r16[16];
-                tmem_ld16(t_acc, r16);
-                tmem_wait16(r16);
-                tc_fence_before();
-                cr = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(r16[0]) + br0)));
-                cg = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(r16[1]) + br1)));
-                cb = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(r16[2]) + br2)));
-            }
-            // -------------------------- compositing (renderer.py:18-26,65-92) ----------------------------------
-            // every row publishes (alpha, r, g, b); the first RT threads of the slot then walk their ray's
-            // SP samples of this tile front to back -- the reference's sequential cumprod order.
-            TC_TRACE(50);
-            {
-                float4* xch = reinterpret_cast<float4*>(smem + XCH_OFFSET + s * 2048);
-                xch[row] = make_float4(1.f - __expf(-sigma), cr, cg, cb);
-                named_bar_sync(1 + s, 128);
-                TC_TRACE(51);
-                if (row < RT) {
-                    if (tile == 0) { cT = 1.f; c0 = c1 = c2 = c3 = c4 = 0.f; }
-                    const int cray = g * RT + row;
-                    if (cray < N) {
-                        float znear = 0.f, zfar = 0.f;
-                        if (FAST) { const float4 r1 = __ldg(reinterpret_cast<const float4*>(io.rays + (size_t)cray * 8) + 1); znear = r1.z; zfar = r1.w; }
-                        for (int sub = 0; sub < SP; ++sub) {
-                            const int sj = tile * SP + sub;
-                            if (sj >= S) break;
-                            const float4 v = xch[sub * RT + row];
-                            float z;
-                            if (FAST) {
-                                const float t = __ldg(io.t_steps + sj);
-                                if (!io.rg.lindisp) z = __fadd_rn(__fmul_rn(znear, 1.f - t), __fmul_rn(zfar, t));
-                                else z = __fdiv_rn(1.f, __fadd_rn(__fmul_rn(__fdiv_rn(1.f, znear), 1.f - t), __fmul_rn(__fdiv_rn(1.f, zfar), t)));
-                            } else {
-                                z = __ldg(io.z + (size_t)cray * S + sj);
-                            }
-                            const float wgt = v.x * cT;
-                            if (io.alpha) io.alpha[(size_t)cray * S + sj] = v.x;
-                            if (io.weights) io.weights[(size_t)cray * S + sj] = wgt;
-                            c0 = fmaf(wgt, v.y, c0); c1 = fmaf(wgt, v.z, c1); c2 = fmaf(wgt, v.w, c2);
-                            c3 = fmaf(wgt, z, c3); c4 += wgt;
-                            cT *= (1.f - v.x) + 1e-10f;
-                        }
-                        if (tile == NT - 1) {
-                            float o0 = c0, o1 = c1, o2 = c2;
-                            if (sc.white_bkgd) { const float bg = 1.f - c4; o0 += bg; o1 += bg; o2 += bg; }
-                            io.rgb[(size_t)cray * 3 + 0] = o0; io.rgb[(size_t)cray * 3 + 1] = o1; io.rgb[(size_t)cray * 3 + 2] = o2;
-                            io.depth[cray] = c3;
+                    // PE cols 0..31 = [x y z | sin(2^k x) for the first 29 of 30].  (part 0 also owns the rgb
+                    // epilogue + compositing of the previous tile, so it gets the light half of the front end)
+                    float v[32];
+                    v[0] = nx; v[1] = ny; v[2] = nz;
+                    float f = 1.f;
+    #pragma unroll
+                    for (int k = 0; k < 10; ++k) {
+    #pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                            if (3 + 3 * k + j < 32) v[3 + 3 * k + j] = __sinf(nd[j] * f);
+                        f *= 2.f;
+                    }
+    #pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4*>(slot + OFF_PE + sw128_offset(row, c * 8)) =
+                            make_uint4(pack_h2(v[c * 8], v[c * 8 + 1]), pack_h2(v[c * 8 + 2], v[c * 8 + 3]),
+                                       pack_h2(v[c * 8 + 4], v[c * 8 + 5]), pack_h2(v[c * 8 + 6], v[c * 8 + 7]));
+                } else {
+                    // all gathers: volume (8) + colour (12) features + view direction -> MISC cols 0..47 ;
+                    // PE cols 32..63 = [sin(512 z) | cos | 1].  This half starts while part 0 is still compositing.
+                    float feat[20], dir[3] = {0.f, 0.f, 0.f};
+    #pragma unroll
+                    for (int i = 0; i < 20; ++i) feat[i] = 0.f;
+                    if (valid) {
+                        view_dir<false>(sh.cams, dx, dy, dz, dir);
+                        sample_volume(sc, nx, ny, nz, feat);
+    #pragma unroll
+                        for (int v = 0; v < 3; ++v) sample_color<false>(sc, sh.cams, v, px, py, pz, feat + 8 + 4 * v);
+                        if (io.input_feat) {
+                            float4* o = reinterpret_cast<float4*>(io.input_feat + si * 20);
+    #pragma unroll
+                            for (int i = 0; i < 5; ++i)
+                                o[i] = make_float4(feat[4 * i], feat[4 * i + 1], feat[4 * i + 2], feat[4 * i + 3]);
                         }
                     }
+                    TC_TRACE(4);
+                    uint8_t* m = slot + OFF_MISC;
+                    *reinterpret_cast<uint4*>(m + sw128_offset(row, 0)) =
+                        make_uint4(pack_h2(feat[0], feat[1]), pack_h2(feat[2], feat[3]), pack_h2(feat[4], feat[5]), pack_h2(feat[6], feat[7]));
+                    *reinterpret_cast<uint4*>(m + sw128_offset(row, 8)) =
+                        make_uint4(pack_h2(feat[8], feat[9]), pack_h2(feat[10], feat[11]), pack_h2(feat[12], feat[13]), pack_h2(feat[14], feat[15]));
+                    *reinterpret_cast<uint4*>(m + sw128_offset(row, 16)) =
+                        make_uint4(pack_h2(feat[16], feat[17]), pack_h2(feat[18], feat[19]), pack_h2(1.f, 0.f), 0u);
+                    *reinterpret_cast<uint4*>(m + sw128_offset(row, 24)) = make_uint4(0u, 0u, 0u, 0u);
+                    *reinterpret_cast<uint4*>(m + sw128_offset(row, 32)) =
+                        make_uint4(pack_h2(dir[0], dir[1]), pack_h2(dir[2], 1.f), 0u, 0u);
+                    *reinterpret_cast<uint4*>(m + sw128_offset(row, 40)) = make_uint4(0u, 0u, 0u, 0u);
+                    TC_TRACE(5);
+                    float v[32];
+                    v[0] = __sinf(nz * 512.f);
+                    float f = 1.f;
+    #pragma unroll
+                    for (int k = 0; k < 10; ++k) {
+    #pragma unroll
+                        for (int j = 0; j < 3; ++j) v[1 + 3 * k + j] = __cosf(nd[j] * f);
+                        f *= 2.f;
+                    }
+                    v[31] = 1.f;
+    #pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4*>(slot + OFF_PE + sw128_offset(row, 32 + c * 8)) =
+                            make_uint4(pack_h2(v[c * 8], v[c * 8 + 1]), pack_h2(v[c * 8 + 2], v[c * 8 + 3]),
+                                       pack_h2(v[c * 8 + 4], v[c * 8 + 5]), pack_h2(v[c * 8 + 6], v[c * 8 + 7]));
                 }
-                TC_TRACE(53);
+                fence_proxy_async();
+                TC_TRACE(2);
             }
+            if (act_cur) {
+                if (part == 1) {
+                    mbar_wait(&sh.acc_ready[s], par_acc); par_acc ^= 1;   // op 8 retired (keeps the barrier phases aligned)
+                } else {
+                    // -------------------------- op 8: rgb ----------------------------------------------------------
+                    float cr, cg, cb;
+                    {
+                        TC_TRACE(48);
+                        mbar_wait(&sh.acc_ready[s], par_acc); par_acc ^= 1;
+                        TC_TRACE(49);
+                        tc_fence_after();
+                        uint32_t r16[16];
+                        tmem_ld16(t_acc, r16);
+                        tmem_wait16(r16);
+                        tc_fence_before();
+                        cr = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(r16[0]) + br0)));
+                        cg = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(r16[1]) + br1)));
+                        cb = __fdividef(1.f, 1.f + __expf(-(__uint_as_float(r16[2]) + br2)));
+                    }
+                    // -------------------------- compositing (renderer.py:18-26,65-92) ----------------------------------
+                    // every row publishes (alpha, r, g, b); the first RT threads of the slot then walk their ray's
+                    // SP samples of this tile front to back -- the reference's sequential cumprod order.
+                    TC_TRACE(50);
+                    {
+                        float4* xch = reinterpret_cast<float4*>(smem + XCH_OFFSET + s * 2048);
+                        xch[row] = make_float4(1.f - __expf(-sigma), cr, cg, cb);
+                        named_bar_sync(1 + s, 128);
+                        TC_TRACE(51);
+                        if (row < RT) {
+                            if (tile_cur == 0) { cT = 1.f; c0 = c1 = c2 = c3 = c4 = 0.f; }
+                            const int cray = g_cur * RT + row;
+                            if (cray < N) {
+                                float znear = 0.f, zfar = 0.f;
+                                if (FAST) { const float4 r1 = __ldg(reinterpret_cast<const float4*>(io.rays + (size_t)cray * 8) + 1); znear = r1.z; zfar = r1.w; }
+                                for (int sub = 0; sub < SP; ++sub) {
+                                    const int sj = tile_cur * SP + sub;
+                                    if (sj >= S) break;
+                                    const float4 v = xch[sub * RT + row];
+                                    float z;
+                                    if (FAST) {
+                                        const float t = __ldg(io.t_steps + sj);
+                                        if (!io.rg.lindisp) z = __fadd_rn(__fmul_rn(znear, 1.f - t), __fmul_rn(zfar, t));
+                                        else z = __fdiv_rn(1.f, __fadd_rn(__fmul_rn(__fdiv_rn(1.f, znear), 1.f - t), __fmul_rn(__fdiv_rn(1.f, zfar), t)));
+                                    } else {
+                                        z = __ldg(io.z + (size_t)cray * S + sj);
+                                    }
+                                    const float wgt = v.x * cT;
+                                    if (io.alpha) io.alpha[(size_t)cray * S + sj] = v.x;
+                                    if (io.weights) io.weights[(size_t)cray * S + sj] = wgt;
+                                    c0 = fmaf(wgt, v.y, c0); c1 = fmaf(wgt, v.z, c1); c2 = fmaf(wgt, v.w, c2);
+                                    c3 = fmaf(wgt, z, c3); c4 += wgt;
+                                    cT *= (1.f - v.x) + 1e-10f;
+                                }
+                                if (tile_cur == NT - 1) {
+                                    float o0 = c0, o1 = c1, o2 = c2;
+                                    if (sc.white_bkgd) { const float bg = 1.f - c4; o0 += bg; o1 += bg; o2 += bg; }
+                                    io.rgb[(size_t)cray * 3 + 0] = o0; io.rgb[(size_t)cray * 3 + 1] = o1; io.rgb[(size_t)cray * 3 + 2] = o2;
+                                    io.depth[cray] = c3;
+                                }
+                            }
+                        }
+                        TC_TRACE(53);
+                    }
+                }
+            }
+            if (act_next) mbar_arrive(&sh.in_ready[s]);
+            g_cur = g; tile_cur = tile; act_cur = act_next;
         }
     } else if (warp == 16) {
         // =========================== MMA issuer ========================================================
@@ -416,8 +432,9 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
             auto dsw = [&](uint32_t addr) { return ((uint64_t)HI_SW << 32) | (uint64_t)(LO_SW | (addr >> 4)); };
             auto dns = [&](uint32_t addr) { return ((uint64_t)HI_NS << 32) | (uint64_t)(LO_NS | (addr >> 4)); };
             uint32_t nchunk_base = 0;                         // global chunk counter at the start of the pass
+            uint32_t op_base = 0;                             // global GEMM-op counter at the start of the pass
 #pragma unroll 1
-            for (int pass = 0; pass < npass; ++pass) {
+            for (int pass = 0; pass < npass; ++pass, op_base += 9) {
                 const bool act[2] = {group_of(pass, 0) < G, group_of(pass, 1) < G};
                 // one generic body per (op, slot), driven by the op tables (kept small on purpose: this code
                 // runs once per pass and must not evict the epilogue loop from the instruction cache)
@@ -464,7 +481,7 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                                 mma_f16(d_acc, dsw(sl + c_op_bias_aoff[op]), dns(last_stage + c_op_bias_boff[op]), idesc, 1);
                             TC_TRACE(80 + op * 2 + s);
                             mma_commit(&sh.acc_ready[s]);
-                            if (last) mma_commit(&sh.w_free);             // this op's chunks are free once these MMAs retire
+                            if (last) mma_commit(&sh.w_free[(op_base + op) & 3]);   // this op's chunks are free once these MMAs retire
                         }
                         __syncwarp();
                     }
@@ -477,7 +494,7 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
         // =========================== weight loader ========================================================
         if (elect_one()) {
             uint8_t* ring = smem + RING_OFFSET;
-            uint32_t n = 0, ops_freed = 0;                  // chunks issued, w_free phases consumed
+            uint32_t n = 0;                                 // chunks issued
 #pragma unroll 1
             for (int pass = 0; pass < npass; ++pass) {
 #pragma unroll 1
@@ -486,8 +503,8 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
                     if (n >= (uint32_t)tcw::NSTAGE) {
                         // the stage's previous tenant is chunk n - NSTAGE; wait until its op has been released
                         const uint32_t pn = n - tcw::NSTAGE;
-                        const uint32_t need = (pn / tcw::NCHUNK) * 9 + (uint32_t)c_chunk_op[pn % tcw::NCHUNK];
-                        while (ops_freed <= need) { mbar_wait(&sh.w_free, ops_freed & 1); ++ops_freed; }
+                        const uint32_t need = (pn / tcw::NCHUNK) * 9 + (uint32_t)c_chunk_op[pn % tcw::NCHUNK];   // global op index
+                        mbar_wait(&sh.w_free[need & 3], (need >> 2) & 1);
                     }
                     const uint32_t bytes = (uint32_t)tcw::chunk_bytes(c);
                     mbar_arrive_expect_tx(&sh.w_full[st], bytes);

@@ -33,16 +33,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// Blocking wait.  Each probe suspends in hardware for up to ~1 ms; a barrier that stays incomplete for
+// ~4 s is a pipeline bug, so trap (the launch fails loudly) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, 0x989680;\n\t"
-        "@P1 bra WAIT_DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    const uint32_t addr = smem_u32(bar);
+    for (uint32_t tries = 0;; ++tries) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, 0xF4240;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t"
+            "}\n" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+        if (tries > 4000u) __trap();
+    }
 }
 
 // ---- proxies / fences ------------------------------------------------------------------------

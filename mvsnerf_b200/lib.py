@@ -11,7 +11,7 @@ import os
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmvsnerf_b200.so")
+LIB_PATH = os.environ.get("MVSN_LIB") or os.path.join(HERE, "libmvsnerf_b200.so")   # MVSN_LIB: debug builds only
 
 MLP_FP32, MLP_TC_HALF, MLP_TC_SPLIT = 0, 1, 2
 N_MLP_TENSORS, N_COSTREG_TENSORS = 22, 30
