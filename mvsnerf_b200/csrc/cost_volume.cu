@@ -3,9 +3,9 @@
 //
 // One pass, one thread per voxel (x fastest, so every channel plane is written with fully
 // coalesced 128-byte stores): the homography of the two source views is evaluated in registers,
-// the 32-channel feature maps and the quarter-resolution RGB are gathered from channels-last
-// staging copies (8.6 MB total, L2 resident), and mean/variance over the visible views are formed
-// on the fly.  None of the reference's 600 MB temporaries (warped volumes, sum, sum of squares,
+// the 32-channel feature maps and the quarter-resolution RGB are gathered straight from the planar
+// source maps (8.6 MB total, L2 resident; neighbouring lanes read neighbouring source pixels), and
+// mean/variance over the visible views are formed on the fly.  None of the reference's 600 MB temporaries (warped volumes, sum, sum of squares,
 // the replicated reference volume, the sampling grids) exists.  HBM traffic = the 41-channel
 // result (+ the optional masks): 176 B / voxel.
 #include "common.cuh"
@@ -13,8 +13,8 @@
 namespace mvsn {
 
 struct CostArgs {
-    const float4* small;    // [V][h][w] (r,g,b,0) quarter-resolution normalised images
-    const float* feats_cl;  // [V][h][w][32]
+    const float* small;     // [V][3][h][w] quarter-resolution normalised images (planar)
+    const float* feats;     // [V][32][h][w] FeatureNet output, reference layout (planar)
     const float* proj;      // [V][3][4] device
     const float* depths;
     int V, h, w, D, pad;
@@ -23,36 +23,20 @@ struct CostArgs {
 };
 
 // F.interpolate(imgs, (h, w), mode='bilinear', align_corners=False)  (models.py:859)
-__global__ void downsample_images_kernel(const float* __restrict__ imgs, float4* __restrict__ out,
+__global__ void downsample_images_kernel(const float* __restrict__ imgs, float* __restrict__ out,
                                          int V, int H, int W, int h, int w) {
-    const int n = V * h * w;
+    const int n = V * 3 * h * w;
     const float sy = (float)H / (float)h, sx = (float)W / (float)w;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int v = i / (h * w), r = i - v * h * w, y = r / w, x = r - y * w;
+        const int vc = i / (h * w), r = i - vc * h * w, y = r / w, x = r - y * w;
         float fy = fmaxf(sy * ((float)y + 0.5f) - 0.5f, 0.f), fx = fmaxf(sx * ((float)x + 0.5f) - 0.5f, 0.f);
         int y0 = (int)fy, x0 = (int)fx;
         int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
         float ly = fy - (float)y0, lx = fx - (float)x0;
-        float o[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float* p = imgs + ((size_t)v * 3 + c) * H * W;
-            float top = (1.f - lx) * p[(size_t)y0 * W + x0] + lx * p[(size_t)y0 * W + x1];
-            float bot = (1.f - lx) * p[(size_t)y1 * W + x0] + lx * p[(size_t)y1 * W + x1];
-            o[c] = (1.f - ly) * top + ly * bot;
-        }
-        out[i] = make_float4(o[0], o[1], o[2], 0.f);
-    }
-}
-
-// [V][32][h*w] -> [V][h*w][32]
-__global__ void feats_to_cl_kernel(const float* __restrict__ src, float* __restrict__ dst, int V, int hw) {
-    const long long n = (long long)V * hw * 32;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i & 31);
-        const long long pv = i >> 5;
-        const int v = (int)(pv / hw), p = (int)(pv - (long long)v * hw);
-        dst[i] = __ldg(src + ((size_t)v * 32 + c) * hw + p);
+        const float* p = imgs + (size_t)vc * H * W;
+        float top = (1.f - lx) * p[(size_t)y0 * W + x0] + lx * p[(size_t)y0 * W + x1];
+        float bot = (1.f - lx) * p[(size_t)y1 * W + x0] + lx * p[(size_t)y1 * W + x1];
+        out[i] = (1.f - ly) * top + ly * bot;
     }
 }
 
@@ -90,7 +74,11 @@ __device__ __forceinline__ Taps make_taps(const float* __restrict__ P, float xr,
     return t;
 }
 
-__global__ void __launch_bounds__(256)
+// Thread per voxel, x fastest.  Source maps stay in the reference's planar layout: for one channel and
+// one tap the 32 lanes of a warp read neighbouring source pixels (the homography is locally affine), i.e.
+// one or two 128-byte lines per load instruction, and every output channel plane is written with fully
+// coalesced stores.
+__global__ void __launch_bounds__(256, 3)
 cost_volume_kernel(const CostArgs a) {
     const int hp = a.h + 2 * a.pad, wp = a.w + 2 * a.pad;
     const long long plane = (long long)hp * wp, nvox = plane * a.D;
@@ -104,12 +92,9 @@ cost_volume_kernel(const CostArgs a) {
         const int yp = r / wp, xp = r - yp * wp;
         const int y = yp - a.pad, x = xp - a.pad;
         const bool interior = (unsigned)y < (unsigned)a.h && (unsigned)x < (unsigned)a.w;
+        const int ref_off = interior ? y * a.w + x : 0;
         const float depth = __ldg(a.depths + d);
         float* out = a.cost + i;
-
-        // channels 0:3 -- reference-view RGB, interior only; the border is defined as zero (F5)
-        float4 ref_rgb = interior ? __ldg(a.small + y * a.w + x) : make_float4(0.f, 0.f, 0.f, 0.f);
-        out[0 * nvox] = ref_rgb.x; out[1 * nvox] = ref_rgb.y; out[2 * nvox] = ref_rgb.z;
 
         Taps t[2];
         float nvis = 1.f;
@@ -119,48 +104,40 @@ cost_volume_kernel(const CostArgs a) {
             t[v - 1] = make_taps(s_proj + 12 * v, (float)x, (float)y, depth, a.h, a.w);
             nvis += t[v - 1].mask;
             if (a.masks) a.masks[(size_t)v * nvox + i] = t[v - 1].mask;
-            // channels 3v : 3v+3 -- warped source RGB (models.py:872)
-            float cr = 0.f, cg = 0.f, cb = 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float4 p = __ldg(a.small + (size_t)v * hw + t[v - 1].off[k]);
-                cr = fmaf(p.x, t[v - 1].wgt[k], cr); cg = fmaf(p.y, t[v - 1].wgt[k], cg);
-                cb = fmaf(p.z, t[v - 1].wgt[k], cb);
-            }
-            out[(size_t)(3 * v + 0) * nvox] = cr; out[(size_t)(3 * v + 1) * nvox] = cg;
-            out[(size_t)(3 * v + 2) * nvox] = cb;
         }
         const float inv_n = __fdiv_rn(1.f, nvis);                                 // models.py:889
 
-        // channels 9:41 -- variance of the 32 feature channels over {ref, warped src 1, 2}
-        const float4* fref = reinterpret_cast<const float4*>(a.feats_cl + (size_t)(interior ? y * a.w + x : 0) * 32);
+        // channels 0:9 -- reference RGB (interior only; the border is defined as zero, F5) and warped source RGB
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            float4 rv = interior ? __ldg(fref + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float s1[4] = {rv.x, rv.y, rv.z, rv.w};
-            float s2[4] = {__fmul_rn(rv.x, rv.x), __fmul_rn(rv.y, rv.y), __fmul_rn(rv.z, rv.z), __fmul_rn(rv.w, rv.w)};
+        for (int c = 0; c < 3; ++c) {
+            out[(size_t)c * nvox] = interior ? __ldg(a.small + (size_t)c * hw + ref_off) : 0.f;
 #pragma unroll
             for (int v = 1; v < 3; ++v) {
-                float wv[4] = {0.f, 0.f, 0.f, 0.f};
-                const float4* fv = reinterpret_cast<const float4*>(a.feats_cl + (size_t)v * hw * 32) + g;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float4 p = __ldg(fv + (size_t)t[v - 1].off[k] * 8);
-                    const float wk = t[v - 1].wgt[k];
-                    wv[0] = fmaf(p.x, wk, wv[0]); wv[1] = fmaf(p.y, wk, wv[1]);
-                    wv[2] = fmaf(p.z, wk, wv[2]); wv[3] = fmaf(p.w, wk, wv[3]);
-                }
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    s1[c] = __fadd_rn(s1[c], wv[c]);
-                    s2[c] = __fadd_rn(s2[c], __fmul_rn(wv[c], wv[c]));
-                }
+                const float* p = a.small + (size_t)(v * 3 + c) * hw;
+                float acc = __ldg(p + t[v - 1].off[0]) * t[v - 1].wgt[0];
+                acc = fmaf(__ldg(p + t[v - 1].off[1]), t[v - 1].wgt[1], acc);
+                acc = fmaf(__ldg(p + t[v - 1].off[2]), t[v - 1].wgt[2], acc);
+                acc = fmaf(__ldg(p + t[v - 1].off[3]), t[v - 1].wgt[3], acc);
+                out[(size_t)(3 * v + c) * nvox] = acc;                             // models.py:872
             }
+        }
+        // channels 9:41 -- variance of the 32 feature channels over {ref, warped src 1, 2}
+#pragma unroll 2
+        for (int c = 0; c < 32; ++c) {
+            const float rv = interior ? __ldg(a.feats + (size_t)c * hw + ref_off) : 0.f;
+            float s1 = rv, s2 = __fmul_rn(rv, rv);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float m = __fmul_rn(s1[c], inv_n);
-                out[(size_t)(9 + 4 * g + c) * nvox] = __fsub_rn(__fmul_rn(s2[c], inv_n), __fmul_rn(m, m));
+            for (int v = 1; v < 3; ++v) {
+                const float* p = a.feats + (size_t)(v * 32 + c) * hw;
+                float wv = __ldg(p + t[v - 1].off[0]) * t[v - 1].wgt[0];
+                wv = fmaf(__ldg(p + t[v - 1].off[1]), t[v - 1].wgt[1], wv);
+                wv = fmaf(__ldg(p + t[v - 1].off[2]), t[v - 1].wgt[2], wv);
+                wv = fmaf(__ldg(p + t[v - 1].off[3]), t[v - 1].wgt[3], wv);
+                s1 = __fadd_rn(s1, wv);
+                s2 = __fadd_rn(s2, __fmul_rn(wv, wv));
             }
+            const float m = __fmul_rn(s1, inv_n);
+            out[(size_t)(9 + c) * nvox] = __fsub_rn(__fmul_rn(s2, inv_n), __fmul_rn(m, m));
         }
     }
 }
@@ -172,7 +149,7 @@ using namespace mvsn;
 extern "C" {
 
 size_t mvsn_cost_volume_workspace_bytes(int V, int h, int w) {
-    return (size_t)V * h * w * (4 + 32) * sizeof(float);
+    return (size_t)V * 3 * h * w * sizeof(float);          // quarter-resolution images (planar)
 }
 
 int mvsn_build_cost_volume(const float* imgs, const float* feats, const float* proj, const float* depths,
@@ -187,12 +164,10 @@ int mvsn_build_cost_volume(const float* imgs, const float* feats, const float* p
     MVSN_REQUIRE(workspace_bytes >= mvsn_cost_volume_workspace_bytes(V, h, w), MVSN_EWORKSPACE,
                  "mvsn_build_cost_volume: workspace too small");
     MVSN_REQUIRE(aligned16(workspace), MVSN_EALIGN, "mvsn_build_cost_volume: workspace must be 16-byte aligned");
-    float4* small = static_cast<float4*>(workspace);
-    float* feats_cl = reinterpret_cast<float*>(small + (size_t)V * h * w);
-    downsample_images_kernel<<<cdiv((long long)V * h * w, 256), 256, 0, stream>>>(imgs, small, V, H, W, h, w);
-    feats_to_cl_kernel<<<cdiv((long long)V * h * w * 32, 256), 256, 0, stream>>>(feats, feats_cl, V, h * w);
+    float* small = static_cast<float*>(workspace);
+    downsample_images_kernel<<<cdiv((long long)V * 3 * h * w, 256), 256, 0, stream>>>(imgs, small, V, H, W, h, w);
     CostArgs a;
-    a.small = small; a.feats_cl = feats_cl; a.depths = depths;
+    a.small = small; a.feats = feats; a.depths = depths;
     a.V = V; a.h = h; a.w = w; a.D = D; a.pad = pad; a.cost = cost; a.masks = in_masks;
     a.proj = proj;
     const long long nvox = (long long)D * (h + 2 * pad) * (w + 2 * pad);
