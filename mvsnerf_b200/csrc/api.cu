@@ -126,6 +126,8 @@ static int dispatch_render(const mvsn_render_scene* scene, const SceneDev& sc, c
             return launch_render_fp32(sc, io, fast, static_cast<const float*>(scene->mlp_packed), stream);
         case MVSN_MLP_TC_HALF:
             return launch_render_tc(sc, io, fast, scene->mlp_packed, stream);
+        case MVSN_MLP_TC_SPLIT:
+            return launch_render_tcs(sc, io, fast, scene->mlp_packed, stream);
         default:
             set_error("mlp_mode %d is not available in this build", scene->mlp_mode);
             return MVSN_EUNSUPPORTED;
@@ -146,6 +148,7 @@ size_t mvsn_mlp_packed_bytes(int mode) {
     switch (mode) {
         case MVSN_MLP_FP32: return (size_t)w32::TOTAL * sizeof(float);
         case MVSN_MLP_TC_HALF: return mlp_tc_packed_bytes();
+        case MVSN_MLP_TC_SPLIT: return mlp_tcs_packed_bytes();
         default: return 0;
     }
 }
@@ -162,6 +165,7 @@ int mvsn_mlp_pack(const float* const* w, int mode, void* packed, size_t packed_b
         p.p[i] = w[i];
     }
     if (mode == MVSN_MLP_TC_HALF) return pack_mlp_tc(w, packed, (cudaStream_t)stream);
+    if (mode == MVSN_MLP_TC_SPLIT) return pack_mlp_tcs(w, packed, (cudaStream_t)stream);
     pack_mlp_fp32_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(p, static_cast<float*>(packed));
     MVSN_CUDA_CHECK(cudaGetLastError());
     return MVSN_OK;

@@ -49,6 +49,9 @@ int launch_render_fp32(const SceneDev& sc, const RenderIO& io, bool fast, const 
 int launch_render_tc(const SceneDev& sc, const RenderIO& io, bool fast, const void* wimg, cudaStream_t stream);
 size_t mlp_tc_packed_bytes();
 int pack_mlp_tc(const float* const* w, void* packed, cudaStream_t stream);
+int launch_render_tcs(const SceneDev& sc, const RenderIO& io, bool fast, const void* wimg, cudaStream_t stream);
+size_t mlp_tcs_packed_bytes();
+int pack_mlp_tcs(const float* const* w, void* packed, cudaStream_t stream);
 
 // cam = R p + t ; pix = K cam ; (u, v) = pix.xy / pix.z / (W-1, H-1)     utils.py:120-127
 template <bool PRECISE>

@@ -101,7 +101,7 @@ extern "C" int mvsn_selftest_umma_probe(const void* A, const void* B, int N, int
 
 extern "C" int mvsn_selftest_umma(const void* A, const void* B, const void* Bc, int N, int K, float* D, void* stream) {
     MVSN_REQUIRE(A && B && D, MVSN_ENULL, "mvsn_selftest_umma: NULL argument");
-    MVSN_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && K % 64 == 0 && K >= 64 && K <= 256, MVSN_EBADSHAPE,
+    MVSN_REQUIRE(N % 16 == 0 && N >= 16 && N <= 256 && K % 64 == 0 && K >= 64 && K <= 384, MVSN_EBADSHAPE,
                  "mvsn_selftest_umma: N=%d (16..256, %%16) K=%d (64..256, %%64)", N, K);
     const size_t smem = (size_t)(K / 64) * (128 + N) * 128 + (size_t)N * 32 + 1024;
     MVSN_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -310,3 +310,40 @@ def test_full_frame_tc_half(nets, weights):
     a, _ = backend.render_rays(rays[:100003], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(sc.pad),
                                mlp_mode=lib.MLP_TC_HALF)
     assert torch.equal(a, rgb[:100003])
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32-grade tensor-core mode (tcgen05, 2-term fp16 operand split, 3 MMAs per K-step): fp32 gate 1e-4
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S,nrays", [(128, 2048), (128, 3), (32, 1000), (24, 333), (200, 50), (128, 20000)])
+def test_render_tc_split_vs_oracle(mid_scene, nets, weights, S, nrays):
+    from mvsnerf_b200 import lib
+    sc, vol_ref = mid_scene
+    fn, _ = nets
+    rays = synthetic.scene_rays(sc)
+    g = torch.Generator().manual_seed(S * 1000 + nrays)
+    rays = rays[torch.randperm(rays.shape[0], generator=g)[:nrays]]
+    rgb_ref, depth_ref = orc.render_rays(rays, vol_ref, sc.imgs_raw, sc.pose_source, weights, sc.H, sc.W,
+                                         sc.near_far, float(sc.pad), n_samples=S)
+    d = sc.to(DEV)
+    rgb, depth = backend.render_rays(rays.to(DEV), vol_ref.to(DEV), d.imgs_raw, d.pose_source, fn, sc.near_far,
+                                     float(sc.pad), N_samples=S, mlp_mode=lib.MLP_TC_SPLIT)
+    torch.cuda.synchronize()
+    e = (rgb.cpu() - rgb_ref).abs().max().item()
+    assert e < RGB_TOL, e
+    assert (depth.cpu() - depth_ref).abs().max() < DEPTH_TOL
+
+
+def test_render_tc_split_vs_golden(golden_tiny, nets):
+    from mvsnerf_b200 import lib
+    g = golden_tiny
+    fn, _ = nets
+    rays = g["rays"]
+    pts, z = orc.march_rays(rays, 32)
+    rgb, feat, wts, depth, alpha, _ = backend.rendering(
+        Args, pose_of(g), pts.to(DEV), g["ndc"].to(DEV), z.to(DEV), rays[:, :3].to(DEV), rays[:, 3:6].to(DEV),
+        g["volume"].to(DEV), g["imgs_raw"].to(DEV), network_fn=fn, mlp_mode=lib.MLP_TC_SPLIT)
+    assert (rgb.cpu() - g["rgb"]).abs().max() < RGB_TOL
+    assert (wts.cpu() - g["weights"]).abs().max() < RGB_TOL
+    assert (alpha.cpu() - g["alpha"]).abs().max() < RGB_TOL
+    assert (depth.cpu() - g["depth"]).abs().max() < DEPTH_TOL

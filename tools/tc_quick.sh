@@ -1,6 +1,4 @@
 #!/bin/bash
-mkdir -p gpurun_out/tc
-timeout 120 python -m pytest tests/test_gpu_parity.py -x -q -k "tc_half_vs_oracle" 2>&1 | tail -4
-timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 120 python bench.py --steps 10 --warmup 3 --mode half --no-cpu-baseline 2>&1 | tail -3 | cut -c1-330
-MVSN_LIB=$PWD/mvsnerf_b200/libmvsnerf_b200_trace.so timeout 100 python tools/tc_trace.py > gpurun_out/trace_latest.txt 2>&1; head -1 gpurun_out/trace_latest.txt
+timeout 400 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+timeout 200 python bench.py --steps 5 --warmup 3 --mode split --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_split.json; cut -c1-330 gpurun_out/bench_split.json; python -c "
+import json; d=json.load(open('gpurun_out/bench_split.json')); print('SPLIT', d['ms_per_step'], d['value'], d['e2e']['value'], d.get('parity_vs_fp32_kernel'))"
