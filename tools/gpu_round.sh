@@ -16,8 +16,6 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGE
     python bench.py --steps 2 --warmup 3 --mode $MODE --no-cpu-baseline > $OUT/ncu_launch_run.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_ -s 3 -c 1 -o $OUT/render_$MODE \
     python bench.py --steps 1 --warmup 3 --mode $MODE --no-cpu-baseline > $OUT/ncu_full_run.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv3d_k3_kernel -c 1 -o $OUT/conv0 \
-    python bench.py --steps 1 --warmup 3 --mode $MODE --no-cpu-baseline > $OUT/ncu_conv0_run.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:cost_volume_kernel -c 1 -o $OUT/costvol \
-    python bench.py --steps 1 --warmup 3 --mode $MODE --no-cpu-baseline > $OUT/ncu_costvol_run.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:render_tcs -c 1 -o $OUT/render_split \
+    python bench.py --steps 1 --warmup 3 --mode split --no-cpu-baseline > $OUT/ncu_split_run.log 2>&1
 ls -la $OUT
