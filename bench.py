@@ -225,8 +225,9 @@ def run_ours(args):
 
     # ---- frames: a spiral of target cameras, each rank renders its own frame of every step ------
     n_frames = args.warmup + args.steps
-    path = synthetic.spiral_path(sc, max(n_frames * world, 2))
-    rays_host = [synthetic.scene_rays(sc, path[(i * world + rank) % len(path)]).pin_memory() for i in range(n_frames)]
+    n_distinct = min(n_frames, 16)                     # distinct target cameras kept resident (cycled for long runs)
+    path = synthetic.spiral_path(sc, max(n_distinct * world, 2))
+    rays_host = [synthetic.scene_rays(sc, path[(i * world + rank) % len(path)]).pin_memory() for i in range(n_distinct)]
     rays_dev = [r.to(dev) for r in rays_host]
     rgb = torch.empty(N_RAYS, 3, device=dev)
     depth = torch.empty(N_RAYS, device=dev)
@@ -236,7 +237,7 @@ def run_ours(args):
     launches = [0]
 
     def step(i):
-        backend.render_rays(rays_dev[i], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD),
+        backend.render_rays(rays_dev[i % n_distinct], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD),
                             N_samples=S, mlp_mode=mode, out=(rgb, depth))
         launches[0] += 1
         if world > 1:
@@ -282,13 +283,13 @@ def run_ours(args):
         # ---- e2e: host rays -> H2D -> kernel -> D2H, through the host-buffer call ------------------
         hfr = backend.HostFrameRenderer(N_RAYS, dev)
         for i in range(min(args.warmup, 2)):
-            hfr.render(rays_host[i], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD), N_samples=S,
+            hfr.render(rays_host[i % n_distinct], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD), N_samples=S,
                        mlp_mode=mode)
         barrier()
         e2e_steps = args.steps
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            hfr.render(rays_host[args.warmup + i], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD),
+            hfr.render(rays_host[(args.warmup + i) % n_distinct], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD),
                        N_samples=S, mlp_mode=mode)
             if world > 1:
                 dist.barrier()
