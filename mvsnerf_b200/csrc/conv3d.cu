@@ -115,24 +115,21 @@ __device__ __forceinline__ void store_and_stats(const ConvArgs& a, float (&acc)[
 // ------------------------------------------------------------------------------------------
 // Conv3d k3 p1, stride 1 or 2
 // ------------------------------------------------------------------------------------------
+// (Conv3d layers never take a skip sum -- only the transposed ones do -- so in1 is not read here.)
 template <int CT, int STRIDE, bool IDENT>
 __global__ void __launch_bounds__(128)
 conv3d_k3_kernel(const ConvArgs a) {
     extern __shared__ __align__(16) float s_w[];            // [Cin][27][CT]
-    __shared__ float s_sc[2][kMaxCin], s_sh[2][kMaxCin];
+    __shared__ float s_sc[kMaxCin], s_sh[kMaxCin];
     __shared__ float s_stat[2 * CT];
     const int tid = threadIdx.x, lane = tid & 31;
     const int cg = blockIdx.y;
-    const bool dual = a.in1.x != nullptr;
 
     for (int i = tid; i < a.Cin * 27 * CT; i += 128) {
         const int c = i % CT, r = i / CT;                   // r = ci*27 + tap
         s_w[i] = __ldg(a.w + (size_t)(cg * CT + c) * a.Cin * 27 + r);
     }
-    if (!IDENT) {
-        load_norm(a.in0, a.Cin, s_sc[0], s_sh[0], tid, 128);
-        if (dual) load_norm(a.in1, a.Cin, s_sc[1], s_sh[1], tid, 128);
-    }
+    if (!IDENT) load_norm(a.in0, a.Cin, s_sc, s_sh, tid, 128);
     if (tid < 2 * CT) s_stat[tid] = 0.f;
     __syncthreads();
 
@@ -154,10 +151,8 @@ conv3d_k3_kernel(const ConvArgs a) {
         for (int c = 0; c < CT; ++c) acc[i][c] = 0.f;
 
     for (int ci = 0; ci < a.Cin; ++ci) {
-        const float sc0 = IDENT ? 1.f : s_sc[0][ci], sh0 = IDENT ? 0.f : s_sh[0][ci];
-        const float sc1 = dual ? s_sc[1][ci] : 1.f, sh1 = dual ? s_sh[1][ci] : 0.f;
+        const float sc0 = IDENT ? 1.f : s_sc[ci], sh0 = IDENT ? 0.f : s_sh[ci];
         const float* base0 = a.in0.x + (size_t)ci * ivol;
-        const float* base1 = dual ? a.in1.x + (size_t)ci * ivol : nullptr;
 #pragma unroll
         for (int dz = 0; dz < 3; ++dz) {
             const int zi = z * STRIDE - 1 + dz;
@@ -169,12 +164,10 @@ conv3d_k3_kernel(const ConvArgs a) {
                 // v[0] = input at xin-1, v[1..] = inputs at xin, xin+1, ...
                 float v[STRIDE == 1 ? 6 : 9];
                 float4 c0 = load_row4<IDENT>(base0 + roff, xin, a.Win, row_ok, vec, sc0, sh0);
-                if (dual) c0 = add4(c0, load_row4<false>(base1 + roff, xin, a.Win, row_ok, vec, sc1, sh1));
                 v[1] = c0.x; v[2] = c0.y; v[3] = c0.z; v[4] = c0.w;
                 float last = c0.w;
                 if (STRIDE == 2) {
                     float4 c1 = load_row4<IDENT>(base0 + roff, xin + 4, a.Win, row_ok, vec, sc0, sh0);
-                    if (dual) c1 = add4(c1, load_row4<false>(base1 + roff, xin + 4, a.Win, row_ok, vec, sc1, sh1));
                     v[5] = c1.x; v[6] = c1.y; v[7] = c1.z; v[8] = c1.w;
                     last = c1.w;
                 }
@@ -183,10 +176,7 @@ conv3d_k3_kernel(const ConvArgs a) {
                 if (sx == 0) left = 0.f;
                 else if (lane == 0) {
                     left = 0.f;
-                    if (row_ok) {
-                        left = IDENT ? __ldg(base0 + roff + xin - 1) : act(__ldg(base0 + roff + xin - 1), sc0, sh0);
-                        if (dual) left += act(__ldg(base1 + roff + xin - 1), sc1, sh1);
-                    }
+                    if (row_ok) left = IDENT ? __ldg(base0 + roff + xin - 1) : act(__ldg(base0 + roff + xin - 1), sc0, sh0);
                 }
                 v[0] = left;
                 if (STRIDE == 1) {
@@ -194,10 +184,8 @@ conv3d_k3_kernel(const ConvArgs a) {
                     if (sx == nsx - 1) right = 0.f;
                     else if (lane == 31) {
                         right = 0.f;
-                        if (row_ok && xin + 4 < a.Win) {
+                        if (row_ok && xin + 4 < a.Win)
                             right = IDENT ? __ldg(base0 + roff + xin + 4) : act(__ldg(base0 + roff + xin + 4), sc0, sh0);
-                            if (dual) right += act(__ldg(base1 + roff + xin + 4), sc1, sh1);
-                        }
                     }
                     v[5] = right;
                 }
@@ -221,6 +209,137 @@ conv3d_k3_kernel(const ConvArgs a) {
         }
     }
     store_and_stats<CT>(a, acc, active, z, y, x0, cg, s_stat, tid);
+}
+
+// ------------------------------------------------------------------------------------------
+// conv0 (41 -> 8 on the raw cost volume, 60 % of CostRegNet's FLOPs): register-tiled variant.
+// A thread owns 4 (x) x 2 (y) output voxels x 8 channels, so the four input rows y0-1 .. y0+2 of a
+// depth slice feed both output rows (12 row loads instead of 18 per input channel) and every
+// weight LDS.128 is amortised over 8 voxels.  Requires W % 4 == 0 and H % 2 == 0 (always true
+// at level 0: D, H, W are multiples of 8) -- no scalar / dual-source / normalise paths are compiled
+// in, which removes ~3/4 of the generic kernel's instruction stream.  The next row's 16-byte load is
+// issued before the current row's 192 FMAs.  Accumulation order per output (ci, dz, dy, dx
+// ascending) is the generic kernel's, so results are bit-identical to it.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 4)
+conv0_k3_kernel(const ConvArgs a) {
+    constexpr int CT = 8;
+    extern __shared__ __align__(16) float s_w[];            // [Cin][27][8]
+    __shared__ float s_stat[2 * CT];
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    for (int i = tid; i < a.Cin * 27 * CT; i += 128) {
+        const int c = i % CT, r = i / CT;
+        s_w[i] = __ldg(a.w + (size_t)c * a.Cin * 27 + r);
+    }
+    if (tid < 2 * CT) s_stat[tid] = 0.f;
+    __syncthreads();
+
+    const int W = a.Win, H = a.Hin, D = a.Din;
+    const int nsx = W >> 2, H2 = H >> 1;
+    const long long nstrips = (long long)D * H2 * nsx;
+    const long long sid = (long long)blockIdx.x * 128 + tid;
+    const bool active = sid < nstrips;
+    int z = 0, y0 = 0, sx = 0;
+    if (active) { sx = (int)(sid % nsx); long long r = sid / nsx; y0 = 2 * (int)(r % H2); z = (int)(r / H2); }
+    const int x0 = sx * 4;
+    const size_t iplane = (size_t)H * W, ivol = iplane * D;
+    const bool first = sx == 0, last = sx == nsx - 1;
+
+    // Row r (0..3) of the (ci, dz) slab is input row y0 - 1 + r at depth z - 1 + dz.  Offsets are 32-bit
+    // (the launcher checks Cin * D * H * W < 2^31); validity is a 3-bit depth mask and a 4-bit row mask.
+    const float* __restrict__ in = a.in0.x;
+    const int iplane_i = (int)iplane, ivol_i = (int)ivol;
+    const int off0 = (z - 1) * iplane_i + (y0 - 1) * W + x0;
+    unsigned zmask = 0, ymask = 0;
+    if (active) {
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz) zmask |= ((unsigned)(z - 1 + dz) < (unsigned)D) << dz;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) ymask |= ((unsigned)(y0 - 1 + r) < (unsigned)H) << r;
+    }
+    const bool halo_l = lane == 0 && !first, halo_r = lane == 31 && !last;   // neighbours that are not in this warp
+
+    float acc[2][4][CT];
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < CT; ++c) acc[j][i][c] = 0.f;
+
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 nxt = (zmask & 1u) && (ymask & 1u) ? __ldg(reinterpret_cast<const float4*>(in + off0)) : zero4;
+    for (int ci = 0; ci < a.Cin; ++ci) {
+        const int off_ci = off0 + ci * ivol_i;
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float4 cur = nxt;
+                const int off = off_ci + dz * iplane_i + r * W;
+                const bool ok = ((zmask >> dz) & 1u) && ((ymask >> r) & 1u);
+                {   // prefetch the following row (wraps into the next dz / ci; after the last row, nothing)
+                    const int r2 = (r + 1) & 3, dz2 = r == 3 ? (dz + 1) % 3 : dz;
+                    const bool wrap = r == 3 && dz == 2;
+                    const int off2 = off_ci + (wrap ? ivol_i : 0) + dz2 * iplane_i + r2 * W;
+                    const bool ok2 = ((zmask >> dz2) & 1u) && ((ymask >> r2) & 1u) && !(wrap && ci + 1 == a.Cin);
+                    nxt = zero4;
+                    if (ok2) nxt = __ldg(reinterpret_cast<const float4*>(in + off2));
+                }
+                float hl = 0.f, hr = 0.f;
+                if (halo_l && ok) hl = __ldg(in + off - 1);
+                if (halo_r && ok) hr = __ldg(in + off + 4);
+                const float sl = __shfl_up_sync(0xffffffffu, cur.w, 1);
+                const float sr = __shfl_down_sync(0xffffffffu, cur.x, 1);
+                float v[6];
+                v[0] = (lane == 0 || first) ? hl : sl;
+                v[1] = cur.x; v[2] = cur.y; v[3] = cur.z; v[4] = cur.w;
+                v[5] = (lane == 31 || last) ? hr : sr;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {               // output row y0 + j sees this input row as tap dy = r - j
+                    const int dy = r - j;
+                    if (dy < 0 || dy > 2) continue;
+                    const float* wrow = s_w + ((ci * 27) + dz * 9 + dy * 3) * CT;
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(wrow + dx * CT);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wrow + dx * CT + 4);
+                        const float wv[CT] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) {
+                            const float xin = v[o + dx];
+#pragma unroll
+                            for (int c = 0; c < CT; ++c) acc[j][o][c] = fmaf(xin, wv[c], acc[j][o][c]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    const size_t plane = (size_t)a.Hout * a.Wout, vol = plane * a.Dout;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+        float s = 0.f, q = 0.f;
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                float* o = a.out + (size_t)c * vol + (size_t)z * plane + (size_t)(y0 + j) * a.Wout + x0;
+                *reinterpret_cast<float4*>(o) = make_float4(acc[j][0][c], acc[j][1][c], acc[j][2][c], acc[j][3][c]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { s += acc[j][i][c]; q = fmaf(acc[j][i][c], acc[j][i][c], q); }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, off);
+            q += __shfl_xor_sync(0xffffffffu, q, off);
+        }
+        if (lane == 0) { atomicAdd(&s_stat[2 * c], s); atomicAdd(&s_stat[2 * c + 1], q); }
+    }
+    __syncthreads();
+    if (tid < 2 * CT) atomicAdd(&a.stats_out[tid], (double)s_stat[tid]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -341,6 +460,28 @@ static int launch_conv(const ConvArgs& a, cudaStream_t st) {
     return MVSN_OK;
 }
 
+static int launch_conv0(const ConvArgs& a, cudaStream_t st) {
+    if (a.Cout != 8 || (a.Win & 3) || (a.Hin & 1) || (long long)a.Cin * a.Din * a.Hin * a.Win >= (1ll << 31))
+        return launch_conv<8, 1, true>(a, st);
+    const size_t smem = (size_t)a.Cin * 27 * 8 * sizeof(float);
+    MVSN_CUDA_CHECK(cudaFuncSetAttribute(conv0_k3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long nstrips = (long long)a.Dout * (a.Hout / 2) * (a.Wout / 4);
+    conv0_k3_kernel<<<(unsigned)cdiv(nstrips, 128), 128, smem, st>>>(a);
+    MVSN_CUDA_CHECK(cudaGetLastError());
+    return MVSN_OK;
+}
+
+// Coarse levels have few voxels (level 3 of a 128x176x208 volume: 9152): narrow the per-CTA output-channel
+// tile until the grid covers the SMs about twice (the layers are latency-, not throughput-bound there).
+template <int STRIDE>
+static int launch_conv_auto(const ConvArgs& a, cudaStream_t st) {
+    const long long ctas16 = cdiv((long long)a.Dout * a.Hout * ((a.Wout + 3) / 4), 128) * (a.Cout / 16);
+    const int want = 2 * sm_count();
+    if (ctas16 >= want || a.Cout % 16) return launch_conv<16, STRIDE, false>(a, st);
+    if (ctas16 * 2 >= want) return launch_conv<8, STRIDE, false>(a, st);
+    return launch_conv<4, STRIDE, false>(a, st);
+}
+
 template <int CT>
 static int launch_deconv(const ConvArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)a.Cin * 27 * CT * sizeof(float);
@@ -421,13 +562,13 @@ int mvsn_costreg_forward(const float* const* w, const float* cost, int D, int Hp
     int rc;
     ActSrc cost_src{cost, nullptr, nullptr, nullptr, 1.0};
     const Dims full{D, Hp, Wp};
-    if ((rc = launch_conv<8, 1, true>(args(0, cost_src, none, full), st))) return rc;          // conv0 41->8
-    if ((rc = launch_conv<16, 2, false>(args(1, src(0), none, dims[0]), st))) return rc;       // conv1 8->16 s2
-    if ((rc = launch_conv<16, 1, false>(args(2, src(1), none, dims[1]), st))) return rc;       // conv2 16->16
-    if ((rc = launch_conv<16, 2, false>(args(3, src(2), none, dims[2]), st))) return rc;       // conv3 16->32 s2
-    if ((rc = launch_conv<16, 1, false>(args(4, src(3), none, dims[3]), st))) return rc;       // conv4 32->32
-    if ((rc = launch_conv<16, 2, false>(args(5, src(4), none, dims[4]), st))) return rc;       // conv5 32->64 s2
-    if ((rc = launch_conv<16, 1, false>(args(6, src(5), none, dims[5]), st))) return rc;       // conv6 64->64
+    if ((rc = launch_conv0(args(0, cost_src, none, full), st))) return rc;                     // conv0 41->8
+    if ((rc = launch_conv_auto<2>(args(1, src(0), none, dims[0]), st))) return rc;       // conv1 8->16 s2
+    if ((rc = launch_conv_auto<1>(args(2, src(1), none, dims[1]), st))) return rc;       // conv2 16->16
+    if ((rc = launch_conv_auto<2>(args(3, src(2), none, dims[2]), st))) return rc;       // conv3 16->32 s2
+    if ((rc = launch_conv_auto<1>(args(4, src(3), none, dims[3]), st))) return rc;       // conv4 32->32
+    if ((rc = launch_conv_auto<2>(args(5, src(4), none, dims[4]), st))) return rc;       // conv5 32->64 s2
+    if ((rc = launch_conv_auto<1>(args(6, src(5), none, dims[5]), st))) return rc;       // conv6 64->64
     if ((rc = launch_deconv<16>(args(7, src(6), none, dims[6]), st))) return rc;               // conv7  64->32
     if ((rc = launch_deconv<16>(args(8, src(4), src(7), dims[7]), st))) return rc;             // conv9  (conv4 + .) 32->16
     if ((rc = launch_deconv<8>(args(9, src(2), src(8), dims[8]), st))) return rc;              // conv11 (conv2 + .) 16->8
