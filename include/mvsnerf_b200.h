@@ -44,6 +44,7 @@ extern "C" {
 
 #define MVSN_N_MLP_TENSORS   22 /* network_fn_state_dict, reference models.py:145-222 / SURVEY App. B */
 #define MVSN_N_COSTREG_TENSORS 30 /* 10 x (conv weight, bn gamma, bn beta), models.py:725-769          */
+#define MVSN_N_FEATURENET_TENSORS 26 /* 8 x (conv weight, bn gamma, bn beta) + toplayer (weight, bias)   */
 #define MVSN_VOL_CH          8
 #define MVSN_COST_CH         41
 #define MVSN_FEAT_CH         32
@@ -139,6 +140,20 @@ int mvsn_build_cost_volume(const float* imgs, const float* feats, const float* p
                            const float* depths, int V, int H, int W, int D, int pad,
                            float* cost, float* in_masks, void* workspace, size_t workspace_bytes,
                            void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Feature extraction  (replaces: FeatureNet.forward + ConvBnReLU + InPlaceABN in train mode,
+ *   models.py:661-672,688-722; called from MVSNet.forward models.py:907-909).
+ *   w[26]: device pointers, for each of conv0.0, conv0.1, conv1.0, conv1.1, conv1.2, conv2.0, conv2.1,
+ *          conv2.2 in that order: (conv weight [Cout,Cin,k,k], bn gamma, bn beta); then toplayer.weight
+ *          [32,32,1,1] and toplayer.bias [32].
+ *   imgs [V,3,H,W] (ImageNet-normalised) -> feats [V,32,ceil(H/4),ceil(W/4)].  Batch statistics are taken
+ *   over all V views jointly, as the reference batches them (B*V images through one BN).
+ * ------------------------------------------------------------------------------------- */
+size_t mvsn_featurenet_workspace_bytes(int V, int H, int W);
+int mvsn_featurenet_forward(const float* const* w_host_array_of_device_ptrs, const float* imgs,
+                            int V, int H, int W, float* feats,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Cost regularisation  (replaces: CostRegNet.forward + ConvBnReLU3D + InPlaceABN in train mode,

@@ -38,8 +38,8 @@ N_DEPTH_PLANES = 128     # models.py:914
 class InPlaceABN(nn.Module):
     """BatchNorm + leaky-ReLU(0.01) with the affine weight used as |gamma|+eps (inplace_abn).
 
-    Only used as a PyTorch op inside FeatureNet (left on cuDNN); inside CostRegNet
-    it is a parameter container and the CUDA kernels apply it."""
+    A parameter container inside FeatureNet / CostRegNet (the CUDA kernels apply it while loading the next
+    layer's input); forward() is the plain PyTorch statement of the op for stand-alone use."""
 
     def __init__(self, num_features, eps=1e-5, momentum=0.1, slope=0.01):
         super().__init__()
@@ -76,7 +76,8 @@ class ConvBnReLU3D(nn.Module):
 
 
 class FeatureNet(nn.Module):
-    """models.py:688-722.  Runs on cuDNN through PyTorch ("next" row 3 of SURVEY.md 8(f))."""
+    """models.py:688-722 parameter layout; forward = one C-ABI call (mvsn_featurenet_forward):
+    eight conv + train-mode InPlaceABN layers (statistics over all views jointly) and the 1x1 toplayer."""
 
     def __init__(self):
         super().__init__()
@@ -85,8 +86,31 @@ class FeatureNet(nn.Module):
         self.conv2 = nn.Sequential(ConvBnReLU(16, 32, 5, 2, 2), ConvBnReLU(32, 32), ConvBnReLU(32, 32))
         self.toplayer = nn.Conv2d(32, 32, 1)
 
+    def weight_list(self):
+        out = []
+        for block in (self.conv0, self.conv1, self.conv2):
+            for m in block:
+                out += [m.conv.weight, m.bn.weight, m.bn.bias]
+        return out + [self.toplayer.weight, self.toplayer.bias]
+
     def forward(self, x):
-        return self.toplayer(self.conv2(self.conv1(self.conv0(x))))
+        """x [V,3,H,W] -> [V,32,ceil(H/4),ceil(W/4)]."""
+        if not self.training:
+            raise RuntimeError("FeatureNet is in eval mode: the CUDA path implements batch-statistics BN only "
+                               "(every shipped caller runs MVSNet.train(), SURVEY.md F2)")
+        lib = _lib.load()
+        x = _lib.dev_f32(x.detach(), "FeatureNet input")
+        V, C, H, W = x.shape
+        if C != 3:
+            raise RuntimeError(f"FeatureNet expects [V,3,H,W] images, got {tuple(x.shape)}")
+        ws_bytes = lib.mvsn_featurenet_workspace_bytes(V, H, W)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        feats = torch.empty(V, 32, (H + 3) // 4, (W + 3) // 4, dtype=torch.float32, device=x.device)
+        weights = [_lib.dev_f32(w.detach(), "FeatureNet weight") for w in self.weight_list()]
+        with torch.cuda.device(x.device):
+            _lib.check(lib.mvsn_featurenet_forward(_lib.ptr_array(weights), _lib.ptr(x), V, H, W, _lib.ptr(feats),
+                                                   _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "mvsn_featurenet_forward")
+        return feats
 
 
 class CostRegNet(nn.Module):
@@ -176,8 +200,7 @@ class MVSNet(nn.Module):
         if not imgs.is_cuda:
             raise RuntimeError("MVSNet: inputs must be CUDA tensors; mvsnerf_b200 has no CPU path")
         B, V, _, H, W = imgs.shape
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # fp32 parity: no TF32 convs
-            feats = self.feature(imgs.reshape(B * V, 3, H, W))
+        feats = self.feature(imgs.reshape(B * V, 3, H, W))
         feats_l = feats.view(B, V, *feats.shape[1:])
         t = torch.linspace(0.0, 1.0, steps=N_DEPTH_PLANES, device=imgs.device, dtype=imgs.dtype)
         near, far = near_far

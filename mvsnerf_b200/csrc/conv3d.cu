@@ -12,21 +12,9 @@
 // channels; a warp owns 32 consecutive strips, so input rows are fetched with one 16-byte load per
 // lane and the +-1 halo comes from the neighbouring lanes by shuffle.  Weights for the CTA's CT
 // output channels sit in shared memory ([cin][27][CT], read as broadcast LDS.128).
-#include "common.cuh"
+#include "conv_common.cuh"
 
 namespace mvsn {
-
-constexpr float kBnEps = 1e-5f;
-constexpr float kSlope = 0.01f;
-constexpr int kMaxCin = 64;
-
-struct ActSrc {                 // one input tensor of a layer, stored raw + its batch statistics
-    const float* x;             // [C][D][H][W]
-    const double* stats;        // [C][2] sum, sum of squares over `count` voxels; null = plain tensor
-    const float* gamma;         // [C]
-    const float* beta;          // [C]
-    double count;
-};
 
 struct ConvArgs {
     ActSrc in0, in1;            // in1.x == null unless the layer input is a skip sum
@@ -36,48 +24,6 @@ struct ConvArgs {
     float* out;                 // [Cout][Dout][Hout][Wout] raw
     double* stats_out;          // [Cout][2]
 };
-
-__device__ __forceinline__ float act(float x, float sc, float sh) {
-    const float y = fmaf(x, sc, sh);
-    return y > 0.f ? y : y * kSlope;
-}
-
-// per-channel (scale, shift) of a source: y = leaky(x * scale + shift)
-__device__ void load_norm(const ActSrc& s, int C, float* sc, float* sh, int tid, int nthreads) {
-    for (int c = tid; c < C; c += nthreads) {
-        if (s.stats) {
-            const double mean = s.stats[2 * c] / s.count;
-            double var = s.stats[2 * c + 1] / s.count - mean * mean;     // biased, as F.batch_norm(training=True)
-            var = var > 0.0 ? var : 0.0;
-            const double inv = 1.0 / sqrt(var + (double)kBnEps);
-            const double g = fabs((double)s.gamma[c]) + (double)kBnEps;
-            sc[c] = (float)(g * inv);
-            sh[c] = (float)((double)s.beta[c] - mean * g * inv);
-        } else {
-            sc[c] = 1.f; sh[c] = 0.f;
-        }
-    }
-}
-
-template <bool IDENT>   // IDENT: plain tensor (the cost volume), no normalisation / activation
-__device__ __forceinline__ float4 load_row4(const float* __restrict__ row, int x, int W, bool row_ok, bool vec,
-                                            float sc, float sh) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (row_ok) {
-        if (vec && x + 3 < W) {
-            v = __ldg(reinterpret_cast<const float4*>(row + x));
-            if (!IDENT) { v.x = act(v.x, sc, sh); v.y = act(v.y, sc, sh); v.z = act(v.z, sc, sh); v.w = act(v.w, sc, sh); }
-        } else {
-            if (x < W)     v.x = IDENT ? __ldg(row + x)     : act(__ldg(row + x), sc, sh);
-            if (x + 1 < W) v.y = IDENT ? __ldg(row + x + 1) : act(__ldg(row + x + 1), sc, sh);
-            if (x + 2 < W) v.z = IDENT ? __ldg(row + x + 2) : act(__ldg(row + x + 2), sc, sh);
-            if (x + 3 < W) v.w = IDENT ? __ldg(row + x + 3) : act(__ldg(row + x + 3), sc, sh);
-        }
-    }
-    return v;
-}
-
-__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 // write 4 x CT raw outputs + accumulate batch statistics
 template <int CT>
@@ -150,44 +96,78 @@ conv3d_k3_kernel(const ConvArgs a) {
 #pragma unroll
         for (int c = 0; c < CT; ++c) acc[i][c] = 0.f;
 
+    // Rows are software-pipelined: the RAW values of row (ci, dz, dy)+1 are requested before row (ci, dz, dy) is
+    // activated and consumed, so a warp always has one 16/32-byte load in flight behind its FMAs (the coarse
+    // levels run ~2 warps per scheduler and were bound by exposed load latency).  Out-of-range taps must be
+    // zero AFTER the activation (zero padding of the activated tensor), hence the validity masks.
+    bool xok[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xok[i] = xin + i < a.Win;
+    auto row_ptr = [&](int ci, int dz, int dy, bool& ok) -> const float* {
+        const int zi = z * STRIDE - 1 + dz, yi = y * STRIDE - 1 + dy;
+        ok = active && (unsigned)zi < (unsigned)a.Din && (unsigned)yi < (unsigned)a.Hin;
+        return a.in0.x + (size_t)ci * ivol + ((long long)zi * (long long)iplane + (long long)yi * a.Win) + xin;
+    };
+    auto fetch = [&](const float* p, int xo, bool ok) -> float4 {     // raw; never dereferences an invalid address
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+            if (vec && xok[xo + 3]) v = __ldg(reinterpret_cast<const float4*>(p + xo));
+            else {
+                if (xok[xo]) v.x = __ldg(p + xo);
+                if (xok[xo + 1]) v.y = __ldg(p + xo + 1);
+                if (xok[xo + 2]) v.z = __ldg(p + xo + 2);
+                if (xok[xo + 3]) v.w = __ldg(p + xo + 3);
+            }
+        }
+        return v;
+    };
+    const bool halo_l = lane == 0 && sx > 0;
+    const bool halo_r = STRIDE == 1 && lane == 31 && sx < nsx - 1 && xin + 4 < a.Win;
+
+    bool ok_n;
+    const float* p_n = row_ptr(0, 0, 0, ok_n);
+    float4 n0 = fetch(p_n, 0, ok_n), n1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (STRIDE == 2) n1 = fetch(p_n, 4, ok_n);
     for (int ci = 0; ci < a.Cin; ++ci) {
         const float sc0 = IDENT ? 1.f : s_sc[ci], sh0 = IDENT ? 0.f : s_sh[ci];
-        const float* base0 = a.in0.x + (size_t)ci * ivol;
 #pragma unroll
         for (int dz = 0; dz < 3; ++dz) {
-            const int zi = z * STRIDE - 1 + dz;
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
-                const int yi = y * STRIDE - 1 + dy;
-                const bool row_ok = active && (unsigned)zi < (unsigned)a.Din && (unsigned)yi < (unsigned)a.Hin;
-                const size_t roff = (size_t)zi * iplane + (size_t)yi * a.Win;
+                const float4 r0 = n0, r1 = n1;
+                const bool row_ok = ok_n;
+                const float* p = p_n;
+                {
+                    const int dy2 = (dy + 1) % 3, dz2 = dy == 2 ? (dz + 1) % 3 : dz;
+                    const bool wrap = dy == 2 && dz == 2;
+                    p_n = row_ptr(wrap ? ci + 1 : ci, dz2, dy2, ok_n);
+                    if (wrap && ci + 1 == a.Cin) ok_n = false;
+                    n0 = fetch(p_n, 0, ok_n);
+                    if (STRIDE == 2) n1 = fetch(p_n, 4, ok_n);
+                }
+                float hl = 0.f, hr = 0.f;
+                if (halo_l && row_ok) hl = IDENT ? __ldg(p - 1) : act(__ldg(p - 1), sc0, sh0);
+                if (halo_r && row_ok) hr = IDENT ? __ldg(p + 4) : act(__ldg(p + 4), sc0, sh0);
                 // v[0] = input at xin-1, v[1..] = inputs at xin, xin+1, ...
                 float v[STRIDE == 1 ? 6 : 9];
-                float4 c0 = load_row4<IDENT>(base0 + roff, xin, a.Win, row_ok, vec, sc0, sh0);
-                v[1] = c0.x; v[2] = c0.y; v[3] = c0.z; v[4] = c0.w;
-                float last = c0.w;
+                v[1] = (IDENT || !(row_ok && xok[0])) ? r0.x : act(r0.x, sc0, sh0);
+                v[2] = (IDENT || !(row_ok && xok[1])) ? r0.y : act(r0.y, sc0, sh0);
+                v[3] = (IDENT || !(row_ok && xok[2])) ? r0.z : act(r0.z, sc0, sh0);
+                v[4] = (IDENT || !(row_ok && xok[3])) ? r0.w : act(r0.w, sc0, sh0);
+                float last = v[4];
                 if (STRIDE == 2) {
-                    float4 c1 = load_row4<IDENT>(base0 + roff, xin + 4, a.Win, row_ok, vec, sc0, sh0);
-                    v[5] = c1.x; v[6] = c1.y; v[7] = c1.z; v[8] = c1.w;
-                    last = c1.w;
+                    v[5] = (IDENT || !(row_ok && xok[4])) ? r1.x : act(r1.x, sc0, sh0);
+                    v[6] = (IDENT || !(row_ok && xok[5])) ? r1.y : act(r1.y, sc0, sh0);
+                    v[7] = (IDENT || !(row_ok && xok[6])) ? r1.z : act(r1.z, sc0, sh0);
+                    v[8] = (IDENT || !(row_ok && xok[7])) ? r1.w : act(r1.w, sc0, sh0);
+                    last = v[8];
                 }
                 // halo from the neighbouring strips (same row when sx > 0 / sx < nsx-1)
-                float left = __shfl_up_sync(0xffffffffu, last, 1);
-                if (sx == 0) left = 0.f;
-                else if (lane == 0) {
-                    left = 0.f;
-                    if (row_ok) left = IDENT ? __ldg(base0 + roff + xin - 1) : act(__ldg(base0 + roff + xin - 1), sc0, sh0);
-                }
-                v[0] = left;
+                const float sl = __shfl_up_sync(0xffffffffu, last, 1);
+                v[0] = (lane == 0 || sx == 0) ? hl : sl;
                 if (STRIDE == 1) {
-                    float right = __shfl_down_sync(0xffffffffu, c0.x, 1);
-                    if (sx == nsx - 1) right = 0.f;
-                    else if (lane == 31) {
-                        right = 0.f;
-                        if (row_ok && xin + 4 < a.Win)
-                            right = IDENT ? __ldg(base0 + roff + xin + 4) : act(__ldg(base0 + roff + xin + 4), sc0, sh0);
-                    }
-                    v[5] = right;
+                    const float sr = __shfl_down_sync(0xffffffffu, v[1], 1);
+                    v[5] = (lane == 31 || sx == nsx - 1) ? hr : sr;
                 }
                 const float* wrow = s_w + ((ci * 27) + dz * 9 + dy * 3) * CT;
 #pragma unroll

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MVSN_LIB") or os.path.join(HERE, "libmvsnerf_b200.so")   # MVSN_LIB: debug builds only
 
 MLP_FP32, MLP_TC_HALF, MLP_TC_SPLIT = 0, 1, 2
-N_MLP_TENSORS, N_COSTREG_TENSORS = 22, 30
+N_MLP_TENSORS, N_COSTREG_TENSORS, N_FEATURENET_TENSORS = 22, 30, 26
 
 # every symbol include/mvsnerf_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
@@ -22,6 +22,7 @@ EXPORTS = [
     "mvsn_pack_images", "mvsn_volume_to_channels_last", "mvsn_volume_from_channels_last",
     "mvsn_render_samples", "mvsn_render_rays", "mvsn_cost_volume_workspace_bytes",
     "mvsn_build_cost_volume", "mvsn_costreg_workspace_bytes", "mvsn_costreg_forward",
+    "mvsn_featurenet_workspace_bytes", "mvsn_featurenet_forward",
     "mvsn_selftest_umma", "mvsn_debug_set_trace",
 ]
 
@@ -67,12 +68,15 @@ def load() -> C.CDLL:
     lib.mvsn_costreg_workspace_bytes.restype = C.c_size_t
     lib.mvsn_costreg_workspace_bytes.argtypes = [ip, ip, ip]
     lib.mvsn_costreg_forward.argtypes = [C.POINTER(vp), vp, ip, ip, ip, vp, vp, C.c_size_t, vp]
+    lib.mvsn_featurenet_workspace_bytes.restype = C.c_size_t
+    lib.mvsn_featurenet_workspace_bytes.argtypes = [ip, ip, ip]
+    lib.mvsn_featurenet_forward.argtypes = [C.POINTER(vp), vp, ip, ip, ip, vp, vp, C.c_size_t, vp]
     lib.mvsn_debug_set_trace.argtypes = [vp]
     lib.mvsn_debug_set_trace.restype = None
     lib.mvsn_selftest_umma.argtypes = [vp, vp, vp, ip, ip, vp, vp]
     for name in ("mvsn_selftest_umma", "mvsn_mlp_pack", "mvsn_pack_images", "mvsn_volume_to_channels_last",
                  "mvsn_volume_from_channels_last", "mvsn_render_samples", "mvsn_render_rays",
-                 "mvsn_build_cost_volume", "mvsn_costreg_forward"):
+                 "mvsn_build_cost_volume", "mvsn_costreg_forward", "mvsn_featurenet_forward"):
         getattr(lib, name).restype = ip
     _lib = lib
     return lib

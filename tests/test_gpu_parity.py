@@ -98,6 +98,27 @@ def test_cost_volume_vs_golden(golden_tiny, nets):
     assert cost[0, :3, :, :pad].abs().max() == 0        # F5: border of the ref-RGB channels is zero
 
 
+def test_featurenet_vs_golden(golden_tiny, golden_c1, nets):
+    """K-F (mvsn_featurenet_forward) against the unmodified reference's FeatureNet outputs."""
+    _, mvs = nets
+    g = golden_tiny
+    feats = mvs.feature(g["imgs_norm"][0].to(DEV))
+    assert feats.shape == g["feats"].shape
+    assert (feats.cpu() - g["feats"]).abs().max() < 1e-4 * g["feats"].abs().max() + 1e-5
+
+
+@pytest.mark.parametrize("V,H,W", [(3, 128, 160), (3, 36, 52), (2, 30, 34), (1, 17, 23), (4, 8, 12), (3, 4, 4)])
+def test_featurenet_vs_oracle_shapes(nets, weights, V, H, W):
+    """Ragged sizes: widths that are not multiples of 4 at some level (scalar row path), odd sizes
+    (k5 s2 p2 output = ceil(n/2)), a single view, a single strip."""
+    _, mvs = nets
+    x = torch.randn(V, 3, H, W, generator=torch.Generator().manual_seed(V * 100 + H))
+    ref = orc.feature_net(x, weights)
+    out = mvs.feature(x.to(DEV))
+    assert out.shape == ref.shape
+    assert (out.cpu() - ref).abs().max() < 1e-4 * ref.abs().max() + 1e-5
+
+
 def test_costreg_vs_golden(golden_tiny, nets):
     g = golden_tiny
     _, mvs = nets

@@ -29,6 +29,7 @@ def test_library_exports_every_declared_symbol(built):
     assert L.mvsn_mlp_packed_bytes(lib.MLP_FP32) > 126788 * 4
     assert L.mvsn_costreg_workspace_bytes(128, 176, 208) > 400e6
     assert L.mvsn_cost_volume_workspace_bytes(3, 128, 160) == 3 * 3 * 128 * 160 * 4
+    assert L.mvsn_featurenet_workspace_bytes(3, 512, 640) == 4096 + 2 * 3 * 8 * 512 * 640 * 4
 
 
 def test_argument_errors_do_not_need_a_gpu(built):
@@ -37,6 +38,8 @@ def test_argument_errors_do_not_need_a_gpu(built):
     assert rc == -4 and b"NULL" in L.mvsn_last_error()
     rc = L.mvsn_costreg_forward(None, None, 128, 20, 24, None, None, 0, None)
     assert rc == -4
+    rc = L.mvsn_featurenet_forward(None, None, 3, 32, 32, None, None, 0, None)
+    assert rc == -4 and b"featurenet" in L.mvsn_last_error()
     assert L.mvsn_mlp_packed_bytes(99) == 0
 
 
@@ -49,6 +52,8 @@ def test_state_dict_keys_match_reference_checkpoint():
     backend.load_weights_npz(fn, mvs, os.path.join(GOLDEN, "mvsnerf_v0_weights.npz"))   # strict load
     assert len(fn.ordered_params()) == lib.N_MLP_TENSORS
     assert len(mvs.cost_reg_2.weight_list()) == lib.N_COSTREG_TENSORS
+    assert len(mvs.feature.weight_list()) == lib.N_FEATURENET_TENSORS
+    assert mvs.feature.weight_list()[6].shape == (16, 8, 5, 5) and mvs.feature.weight_list()[24].shape == (32, 32, 1, 1)
     assert sum(p.numel() for p in fn.parameters()) == 126788
 
 
