@@ -362,6 +362,14 @@ def run_ours(args):
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }
         line.update(other)
+        tg = os.path.join(ROOT, "profiles", "r01_torch_gpu_baseline_and_fullsize_parity.json")
+        if os.path.exists(tg):                              # recorded by tests/test_gpu_fullsize_oracle.py, not re-timed here
+            rec = json.load(open(tg))
+            line["reference_pytorch_gpu"] = {
+                "value": rec["render_torch_gpu_rays_per_s"], "tf32_value": rec["render_torch_gpu_tf32_rays_per_s"],
+                "unit": "rays/s", "volume_build_ms": rec["volume_build_torch_gpu_ms"],
+                "note": "the oracle's PyTorch modules on one B200 (fp32, 5120-ray chunks), recorded by "
+                        "tests/test_gpu_fullsize_oracle.py into profiles/; the north star's >=10x denominator"}
         if world == 1 and not args.no_cpu_baseline:
             orc, _, weights, sc_cpu = cpu_reference_setup()
             sample = args.cpu_sample
