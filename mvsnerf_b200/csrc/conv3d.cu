@@ -323,17 +323,22 @@ conv0_k3_kernel(const ConvArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------
-// ConvTranspose3d k3 s2 p1 output_padding 1:  out[o] += in[i] * W[k],  o = 2 i - 1 + k
-//   even o: (k=1, i=o/2);  odd o: (k=0, i=(o+1)/2) and (k=2, i=(o-1)/2)
-// A strip of 4 outputs starting at x0 = 4 sx reads inputs ix = 2 sx, 2 sx + 1, 2 sx + 2.
+// ConvTranspose3d k3 s2 p1 output_padding 1:  out[o] += in[i] * W[k],  o = 2 i - 1 + k, Dout = 2 Din.
+// Sub-pixel decomposition: per axis, output 2i takes (k=1, in i); output 2i+1 takes (k=2, in i) and
+// (k=0, in i+1).  So the 2x2x2 output block of input voxel (iz,iy,ix) depends on the 2x2x2 inputs
+// (i .. i+1)^3 and uses each of the 27 taps exactly once: a thread owns one input voxel's output
+// block x 8 channels (64 accumulators), every thread does the same 27 x 8 FMAs per input channel -- no
+// parity divergence, no wasted taps.  Lanes are consecutive ix: the x+1 neighbour comes by shuffle, the
+// 8 output rows are written as float2 (256 B per warp and row).  Two sources (U-Net skip sums) are
+// activated separately and added on load; the next channel's loads are issued before the current FMAs.
 // ------------------------------------------------------------------------------------------
-template <int CT>
 __global__ void __launch_bounds__(128)
-deconv3d_k3s2_kernel(const ConvArgs a) {
+deconv3d_subpixel_kernel(const ConvArgs a) {
+    constexpr int CT = 8;
     extern __shared__ __align__(16) float s_w[];            // [Cin][27][CT]
     __shared__ float s_sc[2][kMaxCin], s_sh[2][kMaxCin];
     __shared__ float s_stat[2 * CT];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int cg = blockIdx.y;
     const bool dual = a.in1.x != nullptr;
 
@@ -346,62 +351,107 @@ deconv3d_k3s2_kernel(const ConvArgs a) {
     if (tid < 2 * CT) s_stat[tid] = 0.f;
     __syncthreads();
 
-    const int nsx = (a.Wout + 3) >> 2;
-    const long long nstrips = (long long)a.Dout * a.Hout * nsx;
-    const long long sid = (long long)blockIdx.x * 128 + tid;
-    const bool active = sid < nstrips;
-    int z = 0, y = 0, sx = 0;
-    if (active) { sx = (int)(sid % nsx); long long r = sid / nsx; y = (int)(r % a.Hout); z = (int)(r / a.Hout); }
-    const int x0 = sx * 4, xi0 = sx * 2;
+    const long long nin = (long long)a.Din * a.Hin * a.Win;
+    const long long vid = (long long)blockIdx.x * 128 + tid;
+    const bool active = vid < nin;
+    int iz = 0, iy = 0, ix = 0;
+    if (active) { ix = (int)(vid % a.Win); long long r = vid / a.Win; iy = (int)(r % a.Hin); iz = (int)(r / a.Hin); }
     const size_t iplane = (size_t)a.Hin * a.Win, ivol = iplane * a.Din;
+    const bool zok = iz + 1 < a.Din, yok = iy + 1 < a.Hin, xok = ix + 1 < a.Win;
+    // the four (dz, dy) rows of this thread's own x column; [j] = dz * 2 + dy
+    bool rok[4] = {active, active && yok, active && zok, active && zok && yok};
+    size_t roff[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) roff[j] = (size_t)(iz + (j >> 1)) * iplane + (size_t)(iy + (j & 1)) * a.Win + ix;
+    const bool need_r = lane == 31 && xok;                  // x+1 neighbour is not in this warp
 
-    // (k, i) pairs along z and y for this output row
-    int kz[2], iz[2], nz, ky[2], iy[2], ny;
-    if ((z & 1) == 0) { nz = 1; kz[0] = 1; iz[0] = z >> 1; kz[1] = 0; iz[1] = 0; }
-    else { nz = 2; kz[0] = 0; iz[0] = (z + 1) >> 1; kz[1] = 2; iz[1] = (z - 1) >> 1; }
-    if ((y & 1) == 0) { ny = 1; ky[0] = 1; iy[0] = y >> 1; ky[1] = 0; iy[1] = 0; }
-    else { ny = 2; ky[0] = 0; iy[0] = (y + 1) >> 1; ky[1] = 2; iy[1] = (y - 1) >> 1; }
+    float acc[8][CT];                                        // [pz*4 + py*2 + px][c]
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+#pragma unroll
+        for (int c = 0; c < CT; ++c) acc[o][c] = 0.f;
 
-    float acc[4][CT];
+    float n0[4], n1[4], r0[4], r1[4];                        // raw prefetch: own column / lane 31's right column
+    auto fetch = [&](int ci) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            n0[j] = n1[j] = r0[j] = r1[j] = 0.f;
+            if (rok[j]) {
+                n0[j] = __ldg(a.in0.x + (size_t)ci * ivol + roff[j]);
+                if (dual) n1[j] = __ldg(a.in1.x + (size_t)ci * ivol + roff[j]);
+                if (need_r) {
+                    r0[j] = __ldg(a.in0.x + (size_t)ci * ivol + roff[j] + 1);
+                    if (dual) r1[j] = __ldg(a.in1.x + (size_t)ci * ivol + roff[j] + 1);
+                }
+            }
+        }
+    };
+    fetch(0);
+    for (int ci = 0; ci < a.Cin; ++ci) {
+        const float sc0 = s_sc[0][ci], sh0 = s_sh[0][ci];
+        const float sc1 = dual ? s_sc[1][ci] : 1.f, sh1 = dual ? s_sh[1][ci] : 0.f;
+        float in[4][2];                                      // [dz*2+dy][dx], activated, zero outside the tensor
 #pragma unroll
-        for (int c = 0; c < CT; ++c) acc[i][c] = 0.f;
-
-    if (active) {
-        for (int ci = 0; ci < a.Cin; ++ci) {
-            const float sc0 = s_sc[0][ci], sh0 = s_sh[0][ci];
-            const float sc1 = dual ? s_sc[1][ci] : 1.f, sh1 = dual ? s_sh[1][ci] : 0.f;
-            const float* base0 = a.in0.x + (size_t)ci * ivol;
-            const float* base1 = dual ? a.in1.x + (size_t)ci * ivol : nullptr;
-            for (int jz = 0; jz < nz; ++jz) {
-                if (iz[jz] >= a.Din) continue;
-                for (int jy = 0; jy < ny; ++jy) {
-                    if (iy[jy] >= a.Hin) continue;
-                    const size_t roff = (size_t)iz[jz] * iplane + (size_t)iy[jy] * a.Win;
-                    float v[3];
+        for (int j = 0; j < 4; ++j) {
+            float v = 0.f, vr = 0.f;
+            if (rok[j]) {
+                v = act(n0[j], sc0, sh0);
+                if (dual) v += act(n1[j], sc1, sh1);
+                if (need_r) { vr = act(r0[j], sc0, sh0); if (dual) vr += act(r1[j], sc1, sh1); }
+            }
+            const float sh = __shfl_down_sync(0xffffffffu, v, 1);
+            in[j][0] = v;
+            in[j][1] = !xok ? 0.f : (lane == 31 ? vr : sh);
+        }
+        if (ci + 1 < a.Cin) fetch(ci + 1);
+        const float* wci = s_w + (size_t)ci * 27 * CT;
+        // per axis the three (d, p, k) combinations: (0,0,1) (0,1,2) (1,1,0)
 #pragma unroll
-                    for (int i = 0; i < 3; ++i) {
-                        v[i] = 0.f;
-                        if (xi0 + i < a.Win) {
-                            v[i] = act(__ldg(base0 + roff + xi0 + i), sc0, sh0);
-                            if (dual) v[i] += act(__ldg(base1 + roff + xi0 + i), sc1, sh1);
-                        }
-                    }
-                    const float* wrow = s_w + ((ci * 27) + kz[jz] * 9 + ky[jy] * 3) * CT;
+        for (int az = 0; az < 3; ++az) {
+            const int dz = az == 2, pz = az != 0, kz = az == 0 ? 1 : (az == 1 ? 2 : 0);
 #pragma unroll
-                    for (int c = 0; c < CT; ++c) {
-                        const float w0 = wrow[c], w1 = wrow[CT + c], w2 = wrow[2 * CT + c];
-                        acc[0][c] = fmaf(v[0], w1, acc[0][c]);                               // x0   : k=1, i=xi0
-                        acc[1][c] = fmaf(v[1], w0, fmaf(v[0], w2, acc[1][c]));               // x0+1 : k=0,i=xi0+1 ; k=2,i=xi0
-                        acc[2][c] = fmaf(v[1], w1, acc[2][c]);                               // x0+2 : k=1, i=xi0+1
-                        acc[3][c] = fmaf(v[2], w0, fmaf(v[1], w2, acc[3][c]));               // x0+3 : k=0,i=xi0+2 ; k=2,i=xi0+1
-                    }
+            for (int ay = 0; ay < 3; ++ay) {
+                const int dy = ay == 2, py = ay != 0, ky = ay == 0 ? 1 : (ay == 1 ? 2 : 0);
+#pragma unroll
+                for (int ax = 0; ax < 3; ++ax) {
+                    const int dx = ax == 2, px = ax != 0, kx = ax == 0 ? 1 : (ax == 1 ? 2 : 0);
+                    const float* wp = wci + (kz * 9 + ky * 3 + kx) * CT;
+                    const float4 w0 = *reinterpret_cast<const float4*>(wp);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+                    const float wv[CT] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    const float x = in[dz * 2 + dy][dx];
+                    const int o = pz * 4 + py * 2 + px;
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) acc[o][c] = fmaf(x, wv[c], acc[o][c]);
                 }
             }
         }
     }
-    store_and_stats<CT>(a, acc, active, z, y, x0, cg, s_stat, tid);
+
+    const size_t plane = (size_t)a.Hout * a.Wout, vol = plane * a.Dout;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+        float s = 0.f, q = 0.f;
+        if (active) {
+            float* o = a.out + (size_t)(cg * CT + c) * vol + (size_t)(2 * iz) * plane + (size_t)(2 * iy) * a.Wout + 2 * ix;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {                   // j = pz*2 + py
+                *reinterpret_cast<float2*>(o + (size_t)(j >> 1) * plane + (size_t)(j & 1) * a.Wout) =
+                    make_float2(acc[j * 2][c], acc[j * 2 + 1][c]);
+                s += acc[j * 2][c] + acc[j * 2 + 1][c];
+                q = fmaf(acc[j * 2][c], acc[j * 2][c], q);
+                q = fmaf(acc[j * 2 + 1][c], acc[j * 2 + 1][c], q);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, off);
+            q += __shfl_xor_sync(0xffffffffu, q, off);
+        }
+        if (lane == 0) { atomicAdd(&s_stat[2 * c], s); atomicAdd(&s_stat[2 * c + 1], q); }
+    }
+    __syncthreads();
+    if (tid < 2 * CT) atomicAdd(&a.stats_out[2 * (cg * CT) + tid], (double)s_stat[tid]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -462,13 +512,12 @@ static int launch_conv_auto(const ConvArgs& a, cudaStream_t st) {
     return launch_conv<4, STRIDE, false>(a, st);
 }
 
-template <int CT>
 static int launch_deconv(const ConvArgs& a, cudaStream_t st) {
-    const size_t smem = (size_t)a.Cin * 27 * CT * sizeof(float);
-    MVSN_CUDA_CHECK(cudaFuncSetAttribute(deconv3d_k3s2_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const long long nstrips = (long long)a.Dout * a.Hout * ((a.Wout + 3) / 4);
-    dim3 grid(cdiv(nstrips, 128), a.Cout / CT);
-    deconv3d_k3s2_kernel<CT><<<grid, 128, smem, st>>>(a);
+    const size_t smem = (size_t)a.Cin * 27 * 8 * sizeof(float);
+    MVSN_CUDA_CHECK(cudaFuncSetAttribute(deconv3d_subpixel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long nin = (long long)a.Din * a.Hin * a.Win;
+    dim3 grid(cdiv(nin, 128), a.Cout / 8);
+    deconv3d_subpixel_kernel<<<grid, 128, smem, st>>>(a);
     MVSN_CUDA_CHECK(cudaGetLastError());
     return MVSN_OK;
 }
@@ -549,9 +598,9 @@ int mvsn_costreg_forward(const float* const* w, const float* cost, int D, int Hp
     if ((rc = launch_conv_auto<1>(args(4, src(3), none, dims[3]), st))) return rc;       // conv4 32->32
     if ((rc = launch_conv_auto<2>(args(5, src(4), none, dims[4]), st))) return rc;       // conv5 32->64 s2
     if ((rc = launch_conv_auto<1>(args(6, src(5), none, dims[5]), st))) return rc;       // conv6 64->64
-    if ((rc = launch_deconv<16>(args(7, src(6), none, dims[6]), st))) return rc;               // conv7  64->32
-    if ((rc = launch_deconv<16>(args(8, src(4), src(7), dims[7]), st))) return rc;             // conv9  (conv4 + .) 32->16
-    if ((rc = launch_deconv<8>(args(9, src(2), src(8), dims[8]), st))) return rc;              // conv11 (conv2 + .) 16->8
+    if ((rc = launch_deconv(args(7, src(6), none, dims[6]), st))) return rc;               // conv7  64->32
+    if ((rc = launch_deconv(args(8, src(4), src(7), dims[7]), st))) return rc;             // conv9  (conv4 + .) 32->16
+    if ((rc = launch_deconv(args(9, src(2), src(8), dims[8]), st))) return rc;              // conv11 (conv2 + .) 16->8
     const long long nvox = full.n();
     finalize_volume_kernel<<<cdiv(nvox, 256) < sm_count() * 8 ? cdiv(nvox, 256) : sm_count() * 8, 256, 0, st>>>(
         src(0), src(9), nvox, reinterpret_cast<float4*>(volume_dhwc));

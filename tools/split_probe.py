@@ -1,3 +1,5 @@
+"""GPU probe: error of the 2-term fp16 operand split (hi*hi + hi*lo + lo*hi) through mvsn_selftest_umma, incl.
+subnormal lo terms and accumulation order -- the measurements quoted in DESIGN.md for MVSN_MLP_TC_SPLIT."""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mvsnerf_b200 import lib

@@ -1,3 +1,5 @@
+"""GPU probe: issue/commit timing of tcgen05.mma for N = 64/128/256 and several K (mvsn_selftest_umma_probe) --
+the per-MMA and per-commit costs quoted in DESIGN.md."""
 import ctypes as C, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mvsnerf_b200 import lib
