@@ -424,14 +424,32 @@ def rendering(args, pose_ref, rays_pts, rays_ndc, depth_candidates, rays_o, rays
                            "(use_color_volume=False, img_feat=None) -- the branch every shipped config uses")
     mode = kwargs.pop("mlp_mode", DEFAULT_MLP_MODE)
     want_aux = kwargs.pop("want_aux", True)
+    N, S = rays_pts.shape[:2]
+    z = depth_candidates.expand(N, S) if depth_candidates.shape != (N, S) else depth_candidates
+    vol_t = volume_feature.feat_volume if isinstance(volume_feature, nn.Module) else volume_feature
+    if torch.is_grad_enabled() and (vol_t.requires_grad or any(p.requires_grad for p in network_fn.parameters())):
+        # training step (fine-tuning, train_mvs_nerf_finetuning_pl.py:164): same kernel forward, gradients for
+        # the MLP parameters and the encoding volume (see _RenderSamplesFn)
+        params = network_fn.ordered_params()
+        rgb, feat, weights, depth, alpha = _RenderSamplesFn.apply(
+            rays_pts, rays_ndc, z, rays_dir, vol_t, imgs, pose_ref["w2cs"], pose_ref["intrinsics"],
+            bool(white_bkgd), mode, network_fn, volume_feature, *params)
+        return rgb, feat, weights, depth, alpha, {}
+    rgb, feat, weights, depth, alpha = _render_samples_kernel(
+        pose_ref, rays_pts, rays_ndc, z, rays_dir, volume_feature, imgs, network_fn, white_bkgd, mode, want_aux)
+    return rgb, feat, weights, depth, alpha, {}
+
+
+def _render_samples_kernel(pose_ref, rays_pts, rays_ndc, z, rays_dir, volume_feature, imgs, network_fn, white_bkgd,
+                           mode, want_aux=True):
+    """One mvsn_render_samples launch (no autograd graph)."""
     lib = _lib.load()
     N, S = rays_pts.shape[:2]
     dev = rays_pts.device
-    pts = _lib.dev_f32(rays_pts, "rays_pts")
-    ndc = _lib.dev_f32(rays_ndc, "rays_ndc")
-    z = _lib.dev_f32(depth_candidates.expand(N, S) if depth_candidates.shape != (N, S) else depth_candidates,
-                     "depth_candidates")
-    dirs = _lib.dev_f32(rays_dir, "rays_dir")
+    pts = _lib.dev_f32(rays_pts.detach(), "rays_pts")
+    ndc = _lib.dev_f32(rays_ndc.detach(), "rays_ndc")
+    z = _lib.dev_f32(z.detach(), "depth_candidates")
+    dirs = _lib.dev_f32(rays_dir.detach(), "rays_dir")
     sc, keep = _make_scene(pose_ref, volume_feature, imgs, network_fn, white_bkgd, mode)
     rgb = torch.empty(N, 3, dtype=torch.float32, device=dev)
     depth = torch.empty(N, dtype=torch.float32, device=dev)
@@ -445,7 +463,82 @@ def rendering(args, pose_ref, rays_pts, rays_ndc, depth_candidates, rays_o, rays
                                            N, S, _lib.ptr(rgb), _lib.ptr(depth), _lib.ptr(weights), _lib.ptr(alpha),
                                            _lib.ptr(feat), _lib.stream_ptr()), "mvsn_render_samples")
     del keep
-    return rgb, feat, weights, depth, alpha, {}
+    return rgb, feat, weights, depth, alpha
+
+
+def _render_samples_torch(pts, ndc, z, rays_dir, vol, imgs, w2cs, intrinsics, nerf, white_bkgd):
+    """Differentiable PyTorch statement of renderer.rendering (renderer.py:138-165) -- used ONLY inside
+    _RenderSamplesFn.backward to obtain gradients; forward values always come from the CUDA kernel."""
+    N, S = pts.shape[:2]
+    _, V, _, H, W = imgs.shape
+    grid = (ndc * 2 - 1.0).view(1, 1, N, S, 3)
+    vfeat = F.grid_sample(vol, grid, mode="bilinear", padding_mode="zeros", align_corners=True)[0, :, 0].permute(1, 2, 0)
+    inv_scale = torch.tensor([W - 1.0, H - 1.0], device=pts.device)
+    cols = []
+    for v in range(V):                                                           # utils.py:300-332
+        cam = pts.reshape(-1, 3) @ w2cs[v, :3, :3].t() + w2cs[v, :3, 3].view(1, 3)
+        pix = cam @ intrinsics[v].t()
+        g = ((pix[:, :2] / pix[:, 2:3] / inv_scale) * 2 - 1.0).view(1, N, S, 2)
+        c = F.grid_sample(imgs[0, v:v + 1], g, mode="bilinear", padding_mode="border", align_corners=True)[0].permute(1, 2, 0)
+        m = ((g[0] > -1.0) & (g[0] < 1.0)).all(-1, keepdim=True).to(c.dtype)
+        cols += [c, m]
+    feat = torch.cat([vfeat] + cols, -1)
+    d = rays_dir / rays_dir.norm(dim=-1, keepdim=True)
+    d = d @ w2cs[0, :3, :3].t()                                                  # renderer.py:111-122
+    raw = nerf(torch.cat([_embed(ndc), feat, d[:, None].expand(-1, S, -1)], -1))
+    alpha = 1.0 - torch.exp(-raw[..., 3])                                        # renderer.py:18-26
+    trans = torch.cumprod(torch.cat([torch.ones_like(alpha[:, :1]), 1.0 - alpha + 1e-10], -1), -1)[:, :-1]
+    weights = alpha * trans
+    rgb = (weights.unsqueeze(-1) * raw[..., :3]).sum(-2)
+    depth = (weights * z).sum(-1)
+    if white_bkgd:
+        rgb = rgb + (1.0 - weights.sum(-1, keepdim=True))
+    return rgb, feat, weights, depth, alpha
+
+
+class _RenderSamplesFn(torch.autograd.Function):
+    """Training-step form of `rendering` (interim).
+
+    forward: the fused CUDA kernel, exactly as in inference (no graph, nothing per-sample kept).
+    backward: gradients w.r.t. the 22 MLP tensors and the encoding volume by re-evaluating the chunk with
+    PyTorch ops under autograd (_render_samples_torch) -- activation memory exists only during backward.
+    A hand-written backward kernel (MLP dgrad/wgrad + trilinear scatter) is the planned replacement; the
+    interface (what is differentiable, what re-packs after an optimiser step) will not change."""
+
+    @staticmethod
+    def forward(ctx, pts, ndc, z, rays_dir, vol, imgs, w2cs, intrinsics, white_bkgd, mode, network_fn, volume_feature,
+                *params):
+        pose = {"w2cs": w2cs, "intrinsics": intrinsics}
+        out = _render_samples_kernel(pose, pts, ndc, z, rays_dir, volume_feature, imgs, network_fn, white_bkgd, mode)
+        ctx.save_for_backward(pts, ndc, z, rays_dir, vol, imgs, w2cs, intrinsics, *params)
+        ctx.white_bkgd, ctx.network_fn = white_bkgd, network_fn
+        return out
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_feat, g_weights, g_depth, g_alpha):
+        pts, ndc, z, rays_dir, vol, imgs, w2cs, intrinsics, *params = ctx.saved_tensors
+        with torch.enable_grad():
+            vol_g = vol.detach().requires_grad_(ctx.needs_input_grad[4])
+            # evaluate through a functional copy of the module so the user's parameters are not touched
+            leaves = [p.detach().requires_grad_(need) for p, need in zip(params, ctx.needs_input_grad[12:])]
+            names = [n for n, _ in _ordered_named_params(ctx.network_fn)]
+            nerf = lambda x: torch.func.functional_call(ctx.network_fn, dict(zip(names, leaves)), (x,))
+            outs = _render_samples_torch(pts.detach(), ndc.detach(), z.detach(), rays_dir.detach(), vol_g, imgs.detach(),
+                                         w2cs.detach(), intrinsics.detach(), nerf, ctx.white_bkgd)
+            pairs = [(o, g) for o, g in zip(outs, (g_rgb, g_feat, g_weights, g_depth, g_alpha))
+                     if g is not None and o.requires_grad]
+            wrt = [t for t in [vol_g] + leaves if t.requires_grad]
+            grads = torch.autograd.grad([o for o, _ in pairs], wrt, [g for _, g in pairs], allow_unused=True) if wrt and pairs else []
+        it = iter(grads)
+        g_vol = next(it) if vol_g.requires_grad and grads else None
+        g_params = [next(it) if (leaf.requires_grad and grads) else None for leaf in leaves]
+        return (None, None, None, None, g_vol, None, None, None, None, None, None, None, *g_params)
+
+
+def _ordered_named_params(network_fn):
+    """(name, parameter) in MVSNeRF.ordered_params() order."""
+    by_id = {id(p): n for n, p in network_fn.named_parameters()}
+    return [(by_id[id(p)], p) for p in network_fn.ordered_params()]
 
 
 _tsteps = {}

@@ -89,3 +89,79 @@ def test_synthetic_scene_contract():
     assert rays.shape == (64 * 96, 8) and float(rays[0, 6]) == pytest.approx(sc.near_far[0])
     sc2 = synthetic.make_scene(64, 96, pad=4, seed=3)
     assert torch.equal(sc.imgs_raw, sc2.imgs_raw)
+
+
+def test_backward_recompute_is_the_oracle_function(weights):
+    """The PyTorch statement that _RenderSamplesFn.backward differentiates is the same function as the
+    oracle's render_samples (values and gradients), checked on the CPU where no kernel is involved."""
+    from oracle import mvsnerf_oracle as orc
+    sc = synthetic.make_scene(32, 32, pad=4, seed=1)
+    vol = torch.randn(1, 8, 16, 16, 16, generator=torch.Generator().manual_seed(2))
+    rays = synthetic.scene_rays(sc)[::37][:24]
+    pts, z = orc.march_rays(rays, 8)
+    ndc = orc.ndc_coords(sc.pose_source["w2cs"][0], sc.pose_source["intrinsics"][0], pts, sc.H, sc.W,
+                         sc.near_far[0], sc.near_far[1], 4.0)
+    fn = backend.MVSNeRF()
+    backend.load_weights_npz(fn, None, os.path.join(GOLDEN, "mvsnerf_v0_weights.npz"))
+    v1 = vol.clone().requires_grad_(True)
+    a = backend._render_samples_torch(pts, ndc, z, rays[:, 3:6], v1, sc.imgs_raw, sc.pose_source["w2cs"],
+                                      sc.pose_source["intrinsics"], fn, True)
+    wt = {k: v.clone().requires_grad_(k.startswith("mlp/")) for k, v in weights.items()}
+    v2 = vol.clone().requires_grad_(True)
+    b = orc.render_samples(pts, ndc, z, rays[:, 3:6], v2, sc.imgs_raw, sc.pose_source, wt, white_bkgd=True)
+    for x, y in zip(a, b):
+        assert (x - y).abs().max() < 1e-5
+    (a[0].sum() + a[3].sum()).backward()
+    (b[0].sum() + b[3].sum()).backward()
+    assert (v1.grad - v2.grad).abs().max() <= 1e-5 * v2.grad.abs().max() + 1e-8
+    for name, p in fn.named_parameters():
+        g = wt["mlp/" + name].grad
+        assert (p.grad - g).abs().max() <= 1e-4 * g.abs().max() + 1e-8, name
+    assert [n for n, _ in backend._ordered_named_params(fn)][:2] == ["nerf.pts_linears.0.weight", "nerf.pts_linears.0.bias"]
+
+
+def test_autograd_plumbing_of_rendering(monkeypatch):
+    """rendering() under autograd: argument/gradient routing of _RenderSamplesFn, exercised on the CPU with the
+    kernel launch stubbed out (the GPU test checks the same against the real kernel and the oracle)."""
+    from oracle import mvsnerf_oracle as orc
+    sc = synthetic.make_scene(32, 32, pad=4, seed=1)
+    rays = synthetic.scene_rays(sc)[::41][:16]
+    pts, z = orc.march_rays(rays, 6)
+    ndc = orc.ndc_coords(sc.pose_source["w2cs"][0], sc.pose_source["intrinsics"][0], pts, sc.H, sc.W,
+                         sc.near_far[0], sc.near_far[1], 4.0)
+    fn = backend.MVSNeRF()
+    backend.load_weights_npz(fn, None, os.path.join(GOLDEN, "mvsnerf_v0_weights.npz"))
+    volume = backend.RefVolume(torch.randn(1, 8, 16, 16, 16, generator=torch.Generator().manual_seed(2)))
+
+    def fake_kernel(pose_ref, rays_pts, rays_ndc, zz, rays_dir, volume_feature, imgs, network_fn, white_bkgd, mode,
+                    want_aux=True):
+        assert not torch.is_grad_enabled()
+        return backend._render_samples_torch(rays_pts, rays_ndc, zz, rays_dir, volume_feature.feat_volume, imgs,
+                                             pose_ref["w2cs"], pose_ref["intrinsics"], network_fn, white_bkgd)
+
+    monkeypatch.setattr(backend, "_render_samples_kernel", fake_kernel)
+
+    class A:
+        use_color_volume = False
+    out = backend.rendering(A(), sc.pose_source, pts, ndc, z, rays[:, :3], rays[:, 3:6], volume_feature=volume,
+                            imgs=sc.imgs_raw, network_fn=fn, white_bkgd=False, perturb=0, N_importance=0)
+    assert len(out) == 6 and out[0].requires_grad and out[5] == {}
+    (out[0].sum() + 0.5 * out[3].sum() + 0.1 * out[2].sum()).backward()
+    got = {n: p.grad.clone() for n, p in fn.named_parameters()}
+    gv = volume.feat_volume.grad.clone()
+    fn.zero_grad(); volume.zero_grad()
+    ref = backend._render_samples_torch(pts, ndc, z, rays[:, 3:6], volume.feat_volume, sc.imgs_raw, sc.pose_source["w2cs"],
+                                        sc.pose_source["intrinsics"], fn, False)
+    (ref[0].sum() + 0.5 * ref[3].sum() + 0.1 * ref[2].sum()).backward()
+    for n, p in fn.named_parameters():
+        assert torch.allclose(got[n], p.grad, rtol=1e-5, atol=1e-8), n
+    assert torch.allclose(gv, volume.feat_volume.grad, rtol=1e-5, atol=1e-9)
+    # only the volume trainable
+    for p in fn.parameters():
+        p.requires_grad_(False)
+    fn.zero_grad(set_to_none=True)
+    volume.zero_grad(set_to_none=True)
+    out = backend.rendering(A(), sc.pose_source, pts, ndc, z, rays[:, :3], rays[:, 3:6], volume_feature=volume,
+                            imgs=sc.imgs_raw, network_fn=fn)
+    out[0].sum().backward()
+    assert volume.feat_volume.grad is not None and all(p.grad is None for p in fn.parameters())
