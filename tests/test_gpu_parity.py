@@ -409,15 +409,17 @@ def test_rendering_gradients_vs_oracle_autograd(mid_scene, weights, mode):
     loss = ((rgb - target.to(DEV)) ** 2).mean() + 0.05 * depth.mean() + 0.01 * w.sum(-1).mean()
     assert abs(loss.item() - loss_ref.item()) < (1e-5 if mode == "fp32" else 2e-3)
     loss.backward()
+    # the upstream gradient 2 (rgb - target) / n carries the forward kernel's own rounding: fp32 ~1e-6, half ~1e-3
+    rel = 2e-4 if mode == "fp32" else 5e-3
     names = dict(fn.named_parameters())
     for k, p in names.items():
         g_ref = wt["mlp/" + k].grad
         assert p.grad is not None, k
         err = (p.grad.cpu() - g_ref).abs().max().item()
-        assert err <= 2e-4 * g_ref.abs().max().item() + 1e-7, (k, err, g_ref.abs().max().item())
+        assert err <= rel * g_ref.abs().max().item() + 1e-7, (k, err, g_ref.abs().max().item())
     gv = volume.feat_volume.grad
     assert gv is not None and gv.shape == vt.grad.shape
-    assert (gv.cpu() - vt.grad).abs().max().item() <= 2e-4 * vt.grad.abs().max().item() + 1e-9
+    assert (gv.cpu() - vt.grad).abs().max().item() <= rel * vt.grad.abs().max().item() + 1e-9
     # validation renders under no_grad stay graph-free
     with torch.no_grad():
         out = backend.rendering(Args(), d.pose_source, pts.to(DEV), ndc.to(DEV), z.to(DEV), rays[:, :3].to(DEV),

@@ -5,7 +5,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/pytest_gpu.log
 tail -5 $OUT/pytest_gpu.log
-cp gpurun_out/torch_gpu_baseline.json $OUT/ 2>/dev/null
+cp gpurun_out/torch_gpu_baseline.json gpurun_out/finetune_step.json $OUT/ 2>/dev/null
 timeout 600 python bench.py --steps 10 --warmup 3 --mode half > $OUT/bench_half.json 2> $OUT/bench_half.err; echo "bench rc=$?"
 python - <<PY
 import json; d=json.load(open("$OUT/bench_half.json")); print(json.dumps({k:d[k] for k in ("value","ms_per_step","volume_build","e2e")}))
