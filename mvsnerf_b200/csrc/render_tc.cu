@@ -163,12 +163,14 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sh.tmem_base;
+#ifdef MVSN_TC_TRACE
     // trace roles: 0..3 = (slot, part) warp 0 lane 0 ; 4 = MMA issuer ; 5 = loader
     long long* tr = nullptr; int tr_n = 0;
     if (io.trace && blockIdx.x == 0 && lane == 0) {
         if (warp < 16 && (warp & 3) == 0) tr = io.trace + (warp >> 2) * 1024;
         else if (warp >= 16) tr = io.trace + (4 + warp - 16) * 1024;
     }
+#endif
 
     // ---- work decomposition (identical in every role) ---------------------------------------------
     const int N = io.N, S = io.S;
