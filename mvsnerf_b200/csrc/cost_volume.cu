@@ -3,9 +3,10 @@
 //
 // One pass, one thread per voxel (x fastest, so every channel plane is written with fully
 // coalesced 128-byte stores): the homography of the two source views is evaluated in registers,
-// the 32-channel feature maps and the quarter-resolution RGB are gathered straight from the planar
-// source maps (8.6 MB total, L2 resident; neighbouring lanes read neighbouring source pixels), and
-// mean/variance over the visible views are formed on the fly.  None of the reference's 600 MB temporaries (warped volumes, sum, sum of squares,
+// the 32-channel feature maps and the quarter-resolution RGB are gathered from channel-QUAD staging
+// copies ([C/4][h][w][4]: one 16-byte load brings 4 channels of a tap, and neighbouring lanes still read
+// neighbouring pixels = contiguous bytes; 8.6 MB total, L2 resident), and mean/variance over the
+// visible views are formed on the fly.  None of the reference's 600 MB temporaries (warped volumes, sum, sum of squares,
 // the replicated reference volume, the sampling grids) exists.  HBM traffic = the 41-channel
 // result (+ the optional masks): 176 B / voxel.
 #include "common.cuh"
@@ -13,8 +14,8 @@
 namespace mvsn {
 
 struct CostArgs {
-    const float* small;     // [V][3][h][w] quarter-resolution normalised images (planar)
-    const float* feats;     // [V][32][h][w] FeatureNet output, reference layout (planar)
+    const float4* small;    // [V][h][w] (r,g,b,0) quarter-resolution normalised images
+    const float4* feats;    // [V][8][h][w] channel quads of the FeatureNet output
     const float* proj;      // [V][3][4] device
     const float* depths;
     int V, h, w, D, pad;
@@ -22,21 +23,37 @@ struct CostArgs {
     float* masks;           // [V][D][hp][wp] or null
 };
 
-// F.interpolate(imgs, (h, w), mode='bilinear', align_corners=False)  (models.py:859)
-__global__ void downsample_images_kernel(const float* __restrict__ imgs, float* __restrict__ out,
+// F.interpolate(imgs, (h, w), mode='bilinear', align_corners=False)  (models.py:859), written as (r,g,b,0) texels
+__global__ void downsample_images_kernel(const float* __restrict__ imgs, float4* __restrict__ out,
                                          int V, int H, int W, int h, int w) {
-    const int n = V * 3 * h * w;
+    const int n = V * h * w;
     const float sy = (float)H / (float)h, sx = (float)W / (float)w;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int vc = i / (h * w), r = i - vc * h * w, y = r / w, x = r - y * w;
+        const int v = i / (h * w), r = i - v * h * w, y = r / w, x = r - y * w;
         float fy = fmaxf(sy * ((float)y + 0.5f) - 0.5f, 0.f), fx = fmaxf(sx * ((float)x + 0.5f) - 0.5f, 0.f);
         int y0 = (int)fy, x0 = (int)fx;
         int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
         float ly = fy - (float)y0, lx = fx - (float)x0;
-        const float* p = imgs + (size_t)vc * H * W;
-        float top = (1.f - lx) * p[(size_t)y0 * W + x0] + lx * p[(size_t)y0 * W + x1];
-        float bot = (1.f - lx) * p[(size_t)y1 * W + x0] + lx * p[(size_t)y1 * W + x1];
-        out[i] = (1.f - ly) * top + ly * bot;
+        float c[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float* p = imgs + (size_t)(v * 3 + k) * H * W;
+            float top = (1.f - lx) * p[(size_t)y0 * W + x0] + lx * p[(size_t)y0 * W + x1];
+            float bot = (1.f - lx) * p[(size_t)y1 * W + x0] + lx * p[(size_t)y1 * W + x1];
+            c[k] = (1.f - ly) * top + ly * bot;
+        }
+        out[i] = make_float4(c[0], c[1], c[2], 0.f);
+    }
+}
+
+// feats [V][32][h][w] (reference layout) -> [V][8][h][w][4]
+__global__ void feats_to_quads_kernel(const float* __restrict__ feats, float4* __restrict__ out, int V, int hw) {
+    const long long n = (long long)V * 8 * hw;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long vq = i / hw;
+        const int px = (int)(i - vq * hw);
+        const float* p = feats + (size_t)vq * 4 * hw + px;
+        out[i] = make_float4(__ldg(p), __ldg(p + hw), __ldg(p + 2 * (size_t)hw), __ldg(p + 3 * (size_t)hw));
     }
 }
 
@@ -86,9 +103,11 @@ cost_volume_kernel(const CostArgs a) {
     __shared__ float s_proj[36];
     if (threadIdx.x < 36) s_proj[threadIdx.x] = __ldg(a.proj + threadIdx.x);
     __syncthreads();
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox; i += (long long)gridDim.x * blockDim.x) {
-        const int d = (int)(i / plane);
-        const int r = (int)(i - (long long)d * plane);
+    // grid = (plane tiles, D): one voxel per thread, the depth index is the block's y coordinate (no 64-bit division)
+    const int d = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < (int)plane) {
+        const long long i = (long long)d * plane + r;
         const int yp = r / wp, xp = r - yp * wp;
         const int y = yp - a.pad, x = xp - a.pad;
         const bool interior = (unsigned)y < (unsigned)a.h && (unsigned)x < (unsigned)a.w;
@@ -107,37 +126,43 @@ cost_volume_kernel(const CostArgs a) {
         }
         const float inv_n = __fdiv_rn(1.f, nvis);                                 // models.py:889
 
+        // the four taps of a 4-channel texel, combined per channel in the reference's tap order (nw, ne, sw, se)
+        auto gather4 = [&](const float4* __restrict__ p, const Taps& tp) -> float4 {
+            const float4 a0 = __ldg(p + tp.off[0]), a1 = __ldg(p + tp.off[1]);
+            const float4 a2 = __ldg(p + tp.off[2]), a3 = __ldg(p + tp.off[3]);
+            float4 r;
+            r.x = fmaf(a3.x, tp.wgt[3], fmaf(a2.x, tp.wgt[2], fmaf(a1.x, tp.wgt[1], a0.x * tp.wgt[0])));
+            r.y = fmaf(a3.y, tp.wgt[3], fmaf(a2.y, tp.wgt[2], fmaf(a1.y, tp.wgt[1], a0.y * tp.wgt[0])));
+            r.z = fmaf(a3.z, tp.wgt[3], fmaf(a2.z, tp.wgt[2], fmaf(a1.z, tp.wgt[1], a0.z * tp.wgt[0])));
+            r.w = fmaf(a3.w, tp.wgt[3], fmaf(a2.w, tp.wgt[2], fmaf(a1.w, tp.wgt[1], a0.w * tp.wgt[0])));
+            return r;
+        };
         // channels 0:9 -- reference RGB (interior only; the border is defined as zero, F5) and warped source RGB
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            out[(size_t)c * nvox] = interior ? __ldg(a.small + (size_t)c * hw + ref_off) : 0.f;
+        {
+            const float4 rr = interior ? __ldg(a.small + ref_off) : make_float4(0.f, 0.f, 0.f, 0.f);
+            out[0] = rr.x; out[(size_t)nvox] = rr.y; out[(size_t)2 * nvox] = rr.z;
 #pragma unroll
             for (int v = 1; v < 3; ++v) {
-                const float* p = a.small + (size_t)(v * 3 + c) * hw;
-                float acc = __ldg(p + t[v - 1].off[0]) * t[v - 1].wgt[0];
-                acc = fmaf(__ldg(p + t[v - 1].off[1]), t[v - 1].wgt[1], acc);
-                acc = fmaf(__ldg(p + t[v - 1].off[2]), t[v - 1].wgt[2], acc);
-                acc = fmaf(__ldg(p + t[v - 1].off[3]), t[v - 1].wgt[3], acc);
-                out[(size_t)(3 * v + c) * nvox] = acc;                             // models.py:872
+                const float4 c = gather4(a.small + (size_t)v * hw, t[v - 1]);                 // models.py:872
+                out[(size_t)(3 * v) * nvox] = c.x; out[(size_t)(3 * v + 1) * nvox] = c.y; out[(size_t)(3 * v + 2) * nvox] = c.z;
             }
         }
-        // channels 9:41 -- variance of the 32 feature channels over {ref, warped src 1, 2}
+        // channels 9:41 -- variance of the 32 feature channels over {ref, warped src 1, 2}, four channels at a time
 #pragma unroll 2
-        for (int c = 0; c < 32; ++c) {
-            const float rv = interior ? __ldg(a.feats + (size_t)c * hw + ref_off) : 0.f;
-            float s1 = rv, s2 = __fmul_rn(rv, rv);
+        for (int q = 0; q < 8; ++q) {
+            const float4 rv4 = interior ? __ldg(a.feats + (size_t)q * hw + ref_off) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 w1 = gather4(a.feats + (size_t)(8 + q) * hw, t[0]);
+            const float4 w2 = gather4(a.feats + (size_t)(16 + q) * hw, t[1]);
+            const float rv[4] = {rv4.x, rv4.y, rv4.z, rv4.w};
+            const float wa[4] = {w1.x, w1.y, w1.z, w1.w}, wb[4] = {w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
-            for (int v = 1; v < 3; ++v) {
-                const float* p = a.feats + (size_t)(v * 32 + c) * hw;
-                float wv = __ldg(p + t[v - 1].off[0]) * t[v - 1].wgt[0];
-                wv = fmaf(__ldg(p + t[v - 1].off[1]), t[v - 1].wgt[1], wv);
-                wv = fmaf(__ldg(p + t[v - 1].off[2]), t[v - 1].wgt[2], wv);
-                wv = fmaf(__ldg(p + t[v - 1].off[3]), t[v - 1].wgt[3], wv);
-                s1 = __fadd_rn(s1, wv);
-                s2 = __fadd_rn(s2, __fmul_rn(wv, wv));
+            for (int k = 0; k < 4; ++k) {
+                float s1 = rv[k], s2 = __fmul_rn(rv[k], rv[k]);
+                s1 = __fadd_rn(s1, wa[k]); s2 = __fadd_rn(s2, __fmul_rn(wa[k], wa[k]));
+                s1 = __fadd_rn(s1, wb[k]); s2 = __fadd_rn(s2, __fmul_rn(wb[k], wb[k]));
+                const float m = __fmul_rn(s1, inv_n);
+                out[(size_t)(9 + 4 * q + k) * nvox] = __fsub_rn(__fmul_rn(s2, inv_n), __fmul_rn(m, m));
             }
-            const float m = __fmul_rn(s1, inv_n);
-            out[(size_t)(9 + c) * nvox] = __fsub_rn(__fmul_rn(s2, inv_n), __fmul_rn(m, m));
         }
     }
 }
@@ -149,7 +174,8 @@ using namespace mvsn;
 extern "C" {
 
 size_t mvsn_cost_volume_workspace_bytes(int V, int h, int w) {
-    return (size_t)V * 3 * h * w * sizeof(float);          // quarter-resolution images (planar)
+    // quarter-resolution (r,g,b,0) texels + channel-quad copy of the feature maps
+    return (size_t)V * h * w * 4 * sizeof(float) + (size_t)V * 32 * h * w * sizeof(float);
 }
 
 int mvsn_build_cost_volume(const float* imgs, const float* feats, const float* proj, const float* depths,
@@ -164,15 +190,19 @@ int mvsn_build_cost_volume(const float* imgs, const float* feats, const float* p
     MVSN_REQUIRE(workspace_bytes >= mvsn_cost_volume_workspace_bytes(V, h, w), MVSN_EWORKSPACE,
                  "mvsn_build_cost_volume: workspace too small");
     MVSN_REQUIRE(aligned16(workspace), MVSN_EALIGN, "mvsn_build_cost_volume: workspace must be 16-byte aligned");
-    float* small = static_cast<float*>(workspace);
-    downsample_images_kernel<<<cdiv((long long)V * 3 * h * w, 256), 256, 0, stream>>>(imgs, small, V, H, W, h, w);
+    float4* small = static_cast<float4*>(workspace);
+    float4* featq = small + (size_t)V * h * w;
+    downsample_images_kernel<<<cdiv((long long)V * h * w, 256), 256, 0, stream>>>(imgs, small, V, H, W, h, w);
+    feats_to_quads_kernel<<<cdiv((long long)V * 8 * h * w, 256), 256, 0, stream>>>(feats, featq, V, h * w);
     CostArgs a;
-    a.small = small; a.feats = feats; a.depths = depths;
+    a.small = small; a.feats = featq; a.depths = depths;
     a.V = V; a.h = h; a.w = w; a.D = D; a.pad = pad; a.cost = cost; a.masks = in_masks;
     a.proj = proj;
     const long long nvox = (long long)D * (h + 2 * pad) * (w + 2 * pad);
-    const int blocks = cdiv(nvox, 256) < sm_count() * 16 ? cdiv(nvox, 256) : sm_count() * 16;
-    cost_volume_kernel<<<blocks, 256, 0, stream>>>(a);
+    MVSN_REQUIRE(D <= 65535 && (long long)(h + 2 * pad) * (w + 2 * pad) < (1ll << 31), MVSN_EBADSHAPE,
+                 "mvsn_build_cost_volume: D=%d or the padded plane is too large", D);
+    dim3 grid(cdiv((long long)(h + 2 * pad) * (w + 2 * pad), 256), D);
+    cost_volume_kernel<<<grid, 256, 0, stream>>>(a);
     MVSN_CUDA_CHECK(cudaGetLastError());
     return MVSN_OK;
 }

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(built):
     assert L.mvsn_abi_version() == 1
     assert L.mvsn_mlp_packed_bytes(lib.MLP_FP32) > 126788 * 4
     assert L.mvsn_costreg_workspace_bytes(128, 176, 208) > 400e6
-    assert L.mvsn_cost_volume_workspace_bytes(3, 128, 160) == 3 * 3 * 128 * 160 * 4
+    assert L.mvsn_cost_volume_workspace_bytes(3, 128, 160) == 3 * 128 * 160 * (4 + 32) * 4
     assert L.mvsn_featurenet_workspace_bytes(3, 512, 640) == 4096 + 2 * 3 * 8 * 512 * 640 * 4
 
 
