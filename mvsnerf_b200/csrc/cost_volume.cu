@@ -91,10 +91,9 @@ __device__ __forceinline__ Taps make_taps(const float* __restrict__ P, float xr,
     return t;
 }
 
-// Thread per voxel, x fastest.  Source maps stay in the reference's planar layout: for one channel and
-// one tap the 32 lanes of a warp read neighbouring source pixels (the homography is locally affine), i.e.
-// one or two 128-byte lines per load instruction, and every output channel plane is written with fully
-// coalesced stores.
+// Thread per voxel, x fastest, grid = (plane tiles, depth planes).  For one tap the 32 lanes of a warp read
+// neighbouring source pixels (the homography is locally affine) = contiguous 16-byte texels of the channel-quad
+// copies, and every output channel plane is written with fully coalesced stores.
 __global__ void __launch_bounds__(256, 3)
 cost_volume_kernel(const CostArgs a) {
     const int hp = a.h + 2 * a.pad, wp = a.w + 2 * a.pad;
