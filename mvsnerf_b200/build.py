@@ -36,6 +36,9 @@ def _sources():
 def _digest() -> str:
     h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
     deps = _sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh"))
+    wip_dir = os.path.join(CSRC, "wip")
+    if os.path.isdir(wip_dir):
+        deps += sorted(os.path.join(wip_dir, f) for f in os.listdir(wip_dir) if f.endswith(".cu"))
     deps.append(os.path.join(os.path.dirname(HERE), "include", "mvsnerf_b200.h"))
     for p in deps:
         with open(p, "rb") as f:
@@ -43,15 +46,18 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build_library(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, trace: bool = False, wip: bool = False) -> str:
     """trace=True builds libmvsnerf_b200_trace.so with the pipeline-timeline hooks compiled in
-    (tools/tc_trace.py loads it through MVSN_LIB); the product library never carries them."""
-    build_dir = BUILD_DIR + ("_trace" if trace else "")
-    lib_path = LIB_PATH.replace(".so", "_trace.so") if trace else LIB_PATH
-    flags = NVCC_FLAGS + (["-DMVSN_TC_TRACE"] if trace else [])
+    (tools/tc_trace.py loads it through MVSN_LIB); the product library never carries them.
+    wip=True builds libmvsnerf_b200_wip.so, which additionally contains csrc/wip/*.cu (round-2 work in progress,
+    reachable as mlp_mode 3 through MVSN_LIB); the product library never contains it either."""
+    suffix = "_trace" if trace else "_wip" if wip else ""
+    build_dir = BUILD_DIR + suffix
+    lib_path = LIB_PATH.replace(".so", suffix + ".so")
+    flags = NVCC_FLAGS + (["-DMVSN_TC_TRACE"] if trace else []) + (["-DMVSN_WIP_PAIR"] if wip else [])
     os.makedirs(build_dir, exist_ok=True)
     stamp = os.path.join(build_dir, "stamp")
-    digest = _digest() + ("trace" if trace else "")
+    digest = _digest() + suffix
     if not force and os.path.exists(lib_path) and os.path.exists(stamp) and open(stamp).read() == digest:
         return lib_path
     nvcc = _nvcc()
@@ -69,8 +75,12 @@ def build_library(force: bool = False, verbose: bool = False, trace: bool = Fals
             print(log)
         return obj
 
+    sources = _sources()
+    if wip:
+        wip_dir = os.path.join(CSRC, "wip")
+        sources += sorted(os.path.join(wip_dir, f) for f in os.listdir(wip_dir) if f.endswith(".cu"))
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        objs = list(ex.map(compile_one, _sources()))
+        objs = list(ex.map(compile_one, sources))
     cmd = [nvcc, "-shared", "-o", lib_path, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -81,5 +91,6 @@ def build_library(force: bool = False, verbose: bool = False, trace: bool = Fals
 
 
 if __name__ == "__main__":
-    path = build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv)
+    path = build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv,
+                         wip="--wip" in sys.argv)
     print(path)

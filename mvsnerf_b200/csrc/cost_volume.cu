@@ -189,6 +189,8 @@ int mvsn_build_cost_volume(const float* imgs, const float* feats, const float* p
     MVSN_REQUIRE(workspace_bytes >= mvsn_cost_volume_workspace_bytes(V, h, w), MVSN_EWORKSPACE,
                  "mvsn_build_cost_volume: workspace too small");
     MVSN_REQUIRE(aligned16(workspace), MVSN_EALIGN, "mvsn_build_cost_volume: workspace must be 16-byte aligned");
+    MVSN_REQUIRE(D <= 65535 && (long long)(h + 2 * pad) * (w + 2 * pad) < (1ll << 31), MVSN_EBADSHAPE,
+                 "mvsn_build_cost_volume: D=%d or the padded plane is too large", D);
     float4* small = static_cast<float4*>(workspace);
     float4* featq = small + (size_t)V * h * w;
     downsample_images_kernel<<<cdiv((long long)V * h * w, 256), 256, 0, stream>>>(imgs, small, V, H, W, h, w);
@@ -197,9 +199,6 @@ int mvsn_build_cost_volume(const float* imgs, const float* feats, const float* p
     a.small = small; a.feats = featq; a.depths = depths;
     a.V = V; a.h = h; a.w = w; a.D = D; a.pad = pad; a.cost = cost; a.masks = in_masks;
     a.proj = proj;
-    const long long nvox = (long long)D * (h + 2 * pad) * (w + 2 * pad);
-    MVSN_REQUIRE(D <= 65535 && (long long)(h + 2 * pad) * (w + 2 * pad) < (1ll << 31), MVSN_EBADSHAPE,
-                 "mvsn_build_cost_volume: D=%d or the padded plane is too large", D);
     dim3 grid(cdiv((long long)(h + 2 * pad) * (w + 2 * pad), 256), D);
     cost_volume_kernel<<<grid, 256, 0, stream>>>(a);
     MVSN_CUDA_CHECK(cudaGetLastError());

@@ -52,6 +52,11 @@ int pack_mlp_tc(const float* const* w, void* packed, cudaStream_t stream);
 int launch_render_tcs(const SceneDev& sc, const RenderIO& io, bool fast, const void* wimg, cudaStream_t stream);
 size_t mlp_tcs_packed_bytes();
 int pack_mlp_tcs(const float* const* w, void* packed, cudaStream_t stream);
+#ifdef MVSN_WIP_PAIR   // round-2 work in progress (csrc/wip/), never part of the product library
+int launch_render_tc_pair(const SceneDev& sc, const RenderIO& io, bool fast, const void* wimg, cudaStream_t stream);
+size_t mlp_tc_pair_packed_bytes();
+int pack_mlp_tc_pair(const float* const* w, void* packed, cudaStream_t stream);
+#endif
 
 // cam = R p + t ; pix = K cam ; (u, v) = pix.xy / pix.z / (W-1, H-1)     utils.py:120-127
 template <bool PRECISE>
