@@ -40,6 +40,8 @@ extern "C" {
 #define MVSN_MLP_FP32        0  /* fp32 FFMA, parity <= 1e-4 RGB Linf (north-star fp32 gate)        */
 #define MVSN_MLP_TC_HALF     1  /* tcgen05 kind::f16 operands, fp32 accumulate, gate 5e-3           */
 #define MVSN_MLP_TC_SPLIT    2  /* tcgen05, 2-term fp16 operand split (3 MMAs), fp32-grade, 1e-4    */
+#define MVSN_MLP_TC_PAIR     3  /* as TC_HALF, on CTA pairs (cta_group::2): weights resident in shared     */
+                                /* memory, activations in tensor memory, views/feature layers folded     */
                                 /* (TC modes take any N_samples; rays are tiled 32 at a time)           */
 
 #define MVSN_N_MLP_TENSORS   22 /* network_fn_state_dict, reference models.py:145-222 / SURVEY App. B */

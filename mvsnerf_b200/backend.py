@@ -8,8 +8,11 @@ Same names, argument meaning and return tuples as apchenstu/mvsnerf (SURVEY.md 8
     RefVolume                                       models.py:935-950
     rendering(args, pose_ref, rays_pts, ...)        renderer.py:138-165
 
-so the reference's Lightning scripts / notebooks run unchanged with
-`from mvsnerf_b200.backend import create_nerf_mvs, rendering, RefVolume`.  The modules keep the
+so the reference's per-scene fine-tuning script (train_mvs_nerf_finetuning_pl.py) and the render notebooks run with
+`from mvsnerf_b200.backend import create_nerf_mvs, rendering, RefVolume`.  What does NOT carry over: end-to-end
+training of the encoder (train_mvs_nerf_pl.py back-propagates through MVSNet): the encoding-volume kernels are
+forward-only, `MVSNet.forward` returns a volume without a graph and says so with a warning when called under
+autograd, and `create_nerf_mvs` therefore leaves the encoder's parameters out of `grad_vars`.  The modules keep the
 reference's parameter names, so `ckpts/mvsnerf-v0.tar` (and fine-tuned checkpoints) load with
 `load_state_dict(strict=True)`.  All arithmetic of the path runs in libmvsnerf_b200.so (hand
 written sm_100a CUDA, bound through ctypes); PyTorch here only owns device memory, streams and
@@ -21,6 +24,7 @@ replaces the notebooks' per-chunk loop of ray_marcher -> get_ndc_coordinate -> r
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 import weakref
 
 import torch
@@ -155,6 +159,10 @@ class CostRegNet(nn.Module):
         return vol.permute(3, 0, 1, 2).unsqueeze(0)
 
 
+class FrozenEncoderWarning(UserWarning):
+    """MVSNet.forward was called under autograd with trainable encoder parameters (see its message)."""
+
+
 class MVSNet(nn.Module):
     """Encoding-volume builder with the reference's call signature (models.py:771-932)."""
 
@@ -199,6 +207,12 @@ class MVSNet(nn.Module):
                 "call .train() first")
         if not imgs.is_cuda:
             raise RuntimeError("MVSNet: inputs must be CUDA tensors; mvsnerf_b200 has no CPU path")
+        if torch.is_grad_enabled() and (imgs.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # train_mvs_nerf_pl.py:113 trains the encoder through this call; the kernels here are forward-only
+            warnings.warn("mvsnerf_b200.MVSNet.forward runs forward-only CUDA kernels: the returned encoding volume "
+                          "carries no autograd graph, so FeatureNet / CostRegNet receive no gradients (the encoder is "
+                          "frozen). Call it under torch.no_grad() (as train_mvs_nerf_finetuning_pl.py:63 does) or "
+                          "freeze the module to silence this.", FrozenEncoderWarning, stacklevel=2)
         B, V, _, H, W = imgs.shape
         feats = self.feature(imgs.reshape(B * V, 3, H, W))
         feats_l = feats.view(B, V, *feats.shape[1:])
@@ -326,12 +340,18 @@ class RefVolume(nn.Module):
 _cache = {}
 
 
+cache_stats = {"hit": 0, "miss": 0}
+
+
 def _cached(kind, t, build):
     """One entry per kind, keyed on the IDENTITY of the caller's tensor object (held by weakref)
-    and its in-place version counter -- never on data_ptr, which the caching allocator recycles."""
+    and its in-place version counter -- never on data_ptr, which the caching allocator recycles.
+    `t` must be the object the CALLER holds (a Parameter, a checkpoint tensor), not a view made here."""
     hit = _cache.get(kind)
     if hit is not None and hit[0]() is t and hit[1] == t._version:
+        cache_stats["hit"] += 1
         return hit[2]
+    cache_stats["miss"] += 1
     val = build()
     _cache[kind] = (weakref.ref(t), t._version, val)
     return val
@@ -343,8 +363,8 @@ def clear_cache():
 
 def _volume_channels_last(volume_feature):
     """Accepts a tensor [1,8,D,Hp,Wp] (any strides) or a RefVolume; returns ([D,Hp,Wp,8] fp32, dims)."""
-    vol = volume_feature.feat_volume if isinstance(volume_feature, nn.Module) else volume_feature
-    vol = vol.detach()
+    owner = volume_feature.feat_volume if isinstance(volume_feature, nn.Module) else volume_feature
+    vol = owner.detach()          # a NEW tensor object every call: the cache below is keyed on `owner`
     if vol.dim() != 5 or vol.shape[0] != 1 or vol.shape[1] != 8:
         raise RuntimeError(f"encoding volume must be [1,8,D,H,W], got {tuple(vol.shape)}")
     if not vol.is_cuda:
@@ -363,7 +383,7 @@ def _volume_channels_last(volume_feature):
                        "mvsn_volume_to_channels_last")
         return dst
 
-    return _cached("volume", vol, build), (D, Hp, Wp)
+    return _cached("volume", owner, build), (D, Hp, Wp)
 
 
 def _images_packed(imgs):
@@ -406,7 +426,10 @@ def _make_scene(pose_ref, volume_feature, imgs, network_fn, white_bkgd, mode):
     return sc, keep
 
 
-DEFAULT_MLP_MODE = _lib.MLP_FP32
+# Default arithmetic of `rendering` / `render_rays`: the fp32-grade tensor-core mode (2-term fp16 operand split,
+# RGB Linf 1.2e-5 vs the reference on every pixel of the 512x640 config -- the same as the FFMA kernel, several
+# times faster).  MLP_FP32 (FFMA) and MLP_TC_HALF / MLP_TC_PAIR (5e-3 tier) are selected with `mlp_mode=`.
+DEFAULT_MLP_MODE = _lib.MLP_TC_SPLIT
 
 
 def rendering(args, pose_ref, rays_pts, rays_ndc, depth_candidates, rays_o, rays_dir,
@@ -417,7 +440,7 @@ def rendering(args, pose_ref, rays_pts, rays_ndc, depth_candidates, rays_o, rays
 
     Extra keyword arguments the reference's callers pass (perturb, N_importance, network_fine,
     use_viewdirs, raw_noise_std, NDC_local) are accepted and ignored, as the reference does.
-    `mlp_mode=` selects the GEMM arithmetic (default fp32); `want_aux=False` skips the three
+    `mlp_mode=` selects the GEMM arithmetic (default: DEFAULT_MLP_MODE, the fp32-grade tensor mode); `want_aux=False` skips the three
     per-sample outputs (they are returned as None)."""
     if pose_ref is None or img_feat is not None or getattr(args, "use_color_volume", False):
         raise RuntimeError("rendering: only the pose_ref / image-gather branch of the reference is implemented "
@@ -645,7 +668,8 @@ def create_nerf_mvs(args, pts_embedder=True, use_mvs=False, dir_embedder=True, d
     encoding_net = None
     if use_mvs:
         encoding_net = MVSNet().to(device)
-        grad_vars += list(encoding_net.parameters())
+        # models.py:622 adds the encoder's parameters here; this encoder is forward-only (no gradients reach it,
+        # see MVSNet.forward), so handing them to the optimiser would only pretend to train them.
     ckpt_path = getattr(args, "ckpt", None)
     if ckpt_path is not None and ckpt_path != "None":
         ckpt = torch.load(ckpt_path, map_location=device, weights_only=False)

@@ -128,10 +128,8 @@ static int dispatch_render(const mvsn_render_scene* scene, const SceneDev& sc, c
             return launch_render_tc(sc, io, fast, scene->mlp_packed, stream);
         case MVSN_MLP_TC_SPLIT:
             return launch_render_tcs(sc, io, fast, scene->mlp_packed, stream);
-#ifdef MVSN_WIP_PAIR
-        case 3:                                              // csrc/wip/render_tc_pair.cu, `build --wip` only
-            return launch_render_tc_pair(sc, io, fast, scene->mlp_packed, stream);
-#endif
+        case MVSN_MLP_TC_PAIR:
+            return launch_render_tc2(sc, io, fast, scene->mlp_packed, stream);
         default:
             set_error("mlp_mode %d is not available in this build", scene->mlp_mode);
             return MVSN_EUNSUPPORTED;
@@ -153,9 +151,7 @@ size_t mvsn_mlp_packed_bytes(int mode) {
         case MVSN_MLP_FP32: return (size_t)w32::TOTAL * sizeof(float);
         case MVSN_MLP_TC_HALF: return mlp_tc_packed_bytes();
         case MVSN_MLP_TC_SPLIT: return mlp_tcs_packed_bytes();
-#ifdef MVSN_WIP_PAIR
-        case 3: return mlp_tc_pair_packed_bytes();
-#endif
+        case MVSN_MLP_TC_PAIR: return mlp_tc2_packed_bytes();
         default: return 0;
     }
 }
@@ -173,9 +169,7 @@ int mvsn_mlp_pack(const float* const* w, int mode, void* packed, size_t packed_b
     }
     if (mode == MVSN_MLP_TC_HALF) return pack_mlp_tc(w, packed, (cudaStream_t)stream);
     if (mode == MVSN_MLP_TC_SPLIT) return pack_mlp_tcs(w, packed, (cudaStream_t)stream);
-#ifdef MVSN_WIP_PAIR
-    if (mode == 3) return pack_mlp_tc_pair(w, packed, (cudaStream_t)stream);
-#endif
+    if (mode == MVSN_MLP_TC_PAIR) return pack_mlp_tc2(w, packed, (cudaStream_t)stream);
     pack_mlp_fp32_kernel<<<64, 256, 0, (cudaStream_t)stream>>>(p, static_cast<float*>(packed));
     MVSN_CUDA_CHECK(cudaGetLastError());
     return MVSN_OK;

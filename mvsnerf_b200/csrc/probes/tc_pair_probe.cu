@@ -9,44 +9,13 @@
 //   * completion multicast to both CTAs' mbarriers, each CTA reading its own 128 accumulator rows.
 // D[256, 128] = A[256, K] * B[128, K]^T, fp16 operands, fp32 accumulate.  tools/umma_pair_probe.py runs it
 // under a timeout and compares with torch; mbar_wait traps instead of hanging.
-#include "common.cuh"
-#include "umma.cuh"
+#include "../common.cuh"
+#include "../umma.cuh"
 
 namespace mvsn {
 using namespace umma;
 
 namespace {
-
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc_pair(uint32_t* holder, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(holder)), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish_pair() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory"); }
-__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(addr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// arrive on the mbarrier at the same shared-memory offset in BOTH CTAs of the pair when the MMAs issued so far retire
-__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
-    const uint16_t mask = 3;
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
-                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
-}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
 umma_pair_probe_kernel(const __half* __restrict__ A, const __half* __restrict__ B, int K, float* __restrict__ D) {

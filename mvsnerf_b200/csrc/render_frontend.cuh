@@ -52,11 +52,9 @@ int pack_mlp_tc(const float* const* w, void* packed, cudaStream_t stream);
 int launch_render_tcs(const SceneDev& sc, const RenderIO& io, bool fast, const void* wimg, cudaStream_t stream);
 size_t mlp_tcs_packed_bytes();
 int pack_mlp_tcs(const float* const* w, void* packed, cudaStream_t stream);
-#ifdef MVSN_WIP_PAIR   // round-2 work in progress (csrc/wip/), never part of the product library
-int launch_render_tc_pair(const SceneDev& sc, const RenderIO& io, bool fast, const void* wimg, cudaStream_t stream);
-size_t mlp_tc_pair_packed_bytes();
-int pack_mlp_tc_pair(const float* const* w, void* packed, cudaStream_t stream);
-#endif
+int launch_render_tc2(const SceneDev& sc, const RenderIO& io, bool fast, const void* wimg, cudaStream_t stream);
+size_t mlp_tc2_packed_bytes();
+int pack_mlp_tc2(const float* const* w, void* packed, cudaStream_t stream);
 
 // cam = R p + t ; pix = K cam ; (u, v) = pix.xy / pix.z / (W-1, H-1)     utils.py:120-127
 template <bool PRECISE>
@@ -141,6 +139,51 @@ __device__ __forceinline__ void sample_volume(const SceneDev& sc, float nx, floa
         out8[2] = fmaf(va[c].z, wgt, out8[2]); out8[3] = fmaf(va[c].w, wgt, out8[3]);
         out8[4] = fmaf(vb[c].x, wgt, out8[4]); out8[5] = fmaf(vb[c].y, wgt, out8[5]);
         out8[6] = fmaf(vb[c].z, wgt, out8[6]); out8[7] = fmaf(vb[c].w, wgt, out8[7]);
+    }
+}
+
+// Same arithmetic as sample_volume, one z-plane (8 x 16-byte loads) in flight at a time: for callers that are
+// not latency-critical and are short of registers (the producer warps of render_tc2.cu).
+__device__ __forceinline__ void sample_volume_2pass(const SceneDev& sc, float nx, float ny, float nz, float* out8) {
+    const int W = sc.Wp, H = sc.Hp, D = sc.D;
+    float ix = ((nx * 2.f - 1.f + 1.f) * 0.5f) * (float)(W - 1);
+    float iy = ((ny * 2.f - 1.f + 1.f) * 0.5f) * (float)(H - 1);
+    float iz = ((nz * 2.f - 1.f + 1.f) * 0.5f) * (float)(D - 1);
+    float x0f = floorf(ix), y0f = floorf(iy), z0f = floorf(iz);
+    float wx[2] = {(x0f + 1.f) - ix, ix - x0f}, wy[2] = {(y0f + 1.f) - iy, iy - y0f}, wz[2] = {(z0f + 1.f) - iz, iz - z0f};
+    const int x0 = (int)fminf(fmaxf(x0f, -2.f), (float)W);
+    const int y0 = (int)fminf(fmaxf(y0f, -2.f), (float)H);
+    const int z0 = (int)fminf(fmaxf(z0f, -2.f), (float)D);
+    int xo[2], yo[2], zo[2];
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        const int x = x0 + d, y = y0 + d, z = z0 + d;
+        if ((unsigned)x >= (unsigned)W) wx[d] = 0.f;
+        if ((unsigned)y >= (unsigned)H) wy[d] = 0.f;
+        if ((unsigned)z >= (unsigned)D) wz[d] = 0.f;
+        xo[d] = min(max(x, 0), W - 1); yo[d] = min(max(y, 0), H - 1); zo[d] = min(max(z, 0), D - 1);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) out8[c] = 0.f;
+#pragma unroll 1
+    for (int zz = 0; zz < 2; ++zz) {
+        float4 va[4], vb[4];
+        const int zsel = zz ? zo[1] : zo[0];
+        const float wzsel = zz ? wz[1] : wz[0];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float4* p = reinterpret_cast<const float4*>(
+                sc.vol + (((size_t)zsel * H + yo[(c >> 1) & 1]) * W + xo[c & 1]) * 8);
+            va[c] = __ldg(p); vb[c] = __ldg(p + 1);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {                      // same accumulation order: x fastest, then y, then z
+            const float wgt = wx[c & 1] * wy[(c >> 1) & 1] * wzsel;
+            out8[0] = fmaf(va[c].x, wgt, out8[0]); out8[1] = fmaf(va[c].y, wgt, out8[1]);
+            out8[2] = fmaf(va[c].z, wgt, out8[2]); out8[3] = fmaf(va[c].w, wgt, out8[3]);
+            out8[4] = fmaf(vb[c].x, wgt, out8[4]); out8[5] = fmaf(vb[c].y, wgt, out8[5]);
+            out8[6] = fmaf(vb[c].z, wgt, out8[6]); out8[7] = fmaf(vb[c].w, wgt, out8[7]);
+        }
     }
 }
 

@@ -90,6 +90,7 @@ umma_selftest_kernel(const __half* __restrict__ A, const __half* __restrict__ B,
 
 using namespace mvsn;
 
+#ifdef MVSN_BUILD_PROBES   // issue/commit timing probe: libmvsnerf_b200_probes.so only (tools/umma_probe.py)
 extern "C" int mvsn_selftest_umma_probe(const void* A, const void* B, int N, int K, float* D, int reps, long long* cycles, void* stream) {
     const size_t smem = (size_t)(K / 64) * (128 + N) * 128 + (size_t)N * 32 + 1024;
     MVSN_CUDA_CHECK(cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -98,6 +99,7 @@ extern "C" int mvsn_selftest_umma_probe(const void* A, const void* B, int N, int
     MVSN_CUDA_CHECK(cudaGetLastError());
     return MVSN_OK;
 }
+#endif
 
 extern "C" int mvsn_selftest_umma(const void* A, const void* B, const void* Bc, int N, int K, float* D, void* stream) {
     MVSN_REQUIRE(A && B && D, MVSN_ENULL, "mvsn_selftest_umma: NULL argument");

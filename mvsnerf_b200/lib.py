@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MVSN_LIB") or os.path.join(HERE, "libmvsnerf_b200.so")   # MVSN_LIB: debug builds only
 
 MLP_FP32, MLP_TC_HALF, MLP_TC_SPLIT = 0, 1, 2
-MLP_TC_PAIR_WIP = 3      # csrc/wip/render_tc_pair.cu: only in libmvsnerf_b200_wip.so (`build --wip`, MVSN_LIB=...); unvalidated
+MLP_TC_PAIR = 3          # csrc/render_tc2.cu
 N_MLP_TENSORS, N_COSTREG_TENSORS, N_FEATURENET_TENSORS = 22, 30, 26
 
 # every symbol include/mvsnerf_b200.h declares (tests check the library exports all of them)

@@ -3,7 +3,7 @@ the per-MMA and per-commit costs quoted in DESIGN.md."""
 import ctypes as C, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from mvsnerf_b200 import lib
-L = lib.load()
+L = C.CDLL(os.path.join(os.path.dirname(lib.LIB_PATH), 'libmvsnerf_b200_probes.so'))   # python -m mvsnerf_b200.build --probes
 L.mvsn_selftest_umma_probe.argtypes = [C.c_void_p]*2 + [C.c_int]*2 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
 for N in (64, 128, 256):
     for K in (64, 128):
