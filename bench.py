@@ -178,9 +178,21 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+MODE_DTYPE = {"fp32": "fp32", "half": "fp16 operands / fp32 accumulate", "pair": "fp16 operands / fp32 accumulate",
+              "split": "2x fp16 split operands / fp32 accumulate"}
+MODE_KERNEL = {"fp32": "render_fp32_kernel", "half": "render_tc_kernel", "pair": "render_tc2_kernel",
+               "split": "render_tcs_kernel"}
+
+
+def _median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2] if xs else None
+
+
 def run_ours(args):
     import torch.distributed as dist
     from mvsnerf_b200 import backend, synthetic, lib
+    from mvsnerf_b200 import distributed as mdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -194,20 +206,36 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    mode = {"fp32": lib.MLP_FP32, "half": lib.MLP_TC_HALF, "split": lib.MLP_TC_SPLIT}[args.mode]
+    modes = {"fp32": lib.MLP_FP32, "half": lib.MLP_TC_HALF, "split": lib.MLP_TC_SPLIT, "pair": lib.MLP_TC_PAIR}
+    mode = modes[args.mode]
 
     fn, mvs = backend.MVSNeRF().to(dev), backend.MVSNet().to(dev).train()
     backend.load_weights_npz(fn, mvs, WEIGHTS)
     sc = synthetic.make_scene(H, W, pad=PAD, seed=0)
     d = sc.to(dev)
+    main = torch.cuda.current_stream()
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
 
     def ev_time(f, reps):
         ts = []
         for _ in range(reps):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a, b = ev(), ev()
             a.record(); f(); b.record(); b.synchronize()
             ts.append(a.elapsed_time(b))
         return ts
+
+    def max_over_ranks(x):
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     # ---- once-per-scene encoding volume (reported, not part of the step) -----------------------
     with torch.no_grad():
@@ -224,6 +252,26 @@ def run_ours(args):
     pk = peaks()
     nvox = 128 * (H // 4 + 2 * PAD) * (W // 4 + 2 * PAD)
 
+    def render(rays, m=mode, out=None, sink=None, n_samples=S):
+        return backend.render_rays(rays, vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD),
+                                   N_samples=n_samples, mlp_mode=m, out=out, sink=sink)
+
+    # ---- frame assembly across ranks: NVLink peer stores from the kernel epilogue, else ONE NCCL all-gather ----
+    assemble, frame, why = "none", None, None
+    if world > 1:
+        assemble = args.assemble
+        if assemble == "peer":
+            ok = 1.0
+            try:
+                frame = mdist.PeerFrame(world * N_RAYS, n_buffers=2)
+            except Exception as e:                                   # no peer access on this box: say so, use NCCL
+                ok, why = 0.0, f"{type(e).__name__}: {e}"
+            t = torch.tensor([ok], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if float(t.item()) < 1.0:
+                frame, assemble = None, "nccl"
+                why = why or "a peer rank could not map the frame buffers"
+
     # ---- frames: a spiral of target cameras, each rank renders its own frame of every step ------
     n_frames = args.warmup + args.steps
     n_distinct = min(n_frames, 16)                     # distinct target cameras kept resident (cycled for long runs)
@@ -232,97 +280,178 @@ def run_ours(args):
     rays_dev = [r.to(dev) for r in rays_host]
     rgb = torch.empty(N_RAYS, 3, device=dev)
     depth = torch.empty(N_RAYS, device=dev)
-    rgb_all = torch.empty(world * N_RAYS, 3, device=dev) if world > 1 else None
-    depth_all = torch.empty(world * N_RAYS, device=dev) if world > 1 else None
+    px_local = torch.empty(N_RAYS, 4, device=dev)
+    px_all = torch.empty(world * N_RAYS, 4, device=dev) if assemble == "nccl" else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                  # > 126 MB L2
     launches = [0]
 
-    def step(i):
-        backend.render_rays(rays_dev[i % n_distinct], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD),
-                            N_samples=S, mlp_mode=mode, out=(rgb, depth))
+    def step(i, m=mode, kev=None):
+        """One step: this rank's frame through the render kernel; at N > 1 the job's frames assembled on every rank."""
+        r = rays_dev[i % n_distinct]
+        if kev:
+            kev[0].record()
+        if assemble == "peer":
+            render(r, m, sink=frame.sink(rank * N_RAYS))
+        else:
+            render(r, m, out=(rgb, depth))
+        if kev:
+            kev[1].record()
         launches[0] += 1
-        if world > 1:
-            dist.all_gather_into_tensor(rgb_all, rgb)
-            dist.all_gather_into_tensor(depth_all, depth)
+        if assemble == "peer":
+            frame.complete()
+            frame.rotate()
+        elif assemble == "nccl":
+            px_local[:, :3].copy_(rgb); px_local[:, 3].copy_(depth)
+            dist.all_gather_into_tensor(px_all, px_local)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def timed_steps(m, n_warm, n_steps):
+        """-> (ms_per_step max over ranks, kernel ms list of THIS rank on the same launches, per-step (kernel, rest) ms)."""
+        for i in range(n_warm):
+            step(i, m)
+        barrier()
+        evs = []
+        for i in range(n_warm, n_warm + n_steps):
+            flush.zero_()                                                          # L2 flush, untimed
+            a, ka, kb, b = ev(), ev(), ev(), ev()
+            a.record(); step(i, m, (ka, kb)); b.record()
+            evs.append((a, ka, kb, b))
+        barrier()
+        tot = sum(a.elapsed_time(b) for a, _, _, b in evs)
+        kern = [ka.elapsed_time(kb) for _, ka, kb, _ in evs]
+        rest = [kb.elapsed_time(b) for _, _, kb, b in evs]
+        return max_over_ranks(tot) / n_steps, kern, rest
 
     with torch.no_grad():
+        sampler = ClockSampler(local)
         for i in range(args.warmup):
             step(i)
         barrier()
-        sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
         launches[0] = 0
-        evs = []
         t_wall0 = time.perf_counter()
-        for i in range(args.warmup, n_frames):
-            flush.zero_()                                                          # L2 flush, untimed
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); step(i); b.record()
-            evs.append((a, b))
-        barrier()
+        ms_per_step, kern_list, rest_list = timed_steps(mode, 0, args.steps)
         t_wall = time.perf_counter() - t_wall0
         clocks = sampler.stop() if rank == 0 else None
         n_launch = launches[0]
-        step_ms = [a.elapsed_time(b) for a, b in evs]
-        total_ms = torch.tensor([sum(step_ms)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-        ms_per_step = float(total_ms.item()) / args.steps
         value = world * N_RAYS / (ms_per_step * 1e-3)
+        kern = sum(kern_list) / len(kern_list)        # the render kernel alone, on the SAME launches as ms_per_step
 
-        # kernel-only duration (no collective, no flush) for the roofline: CUDA events around the launch
-        kern_ms = ev_time(lambda: backend.render_rays(rays_dev[-1], vol, d.imgs_raw, d.pose_source, fn, sc.near_far,
-                                                      float(PAD), N_samples=S, mlp_mode=mode, out=(rgb, depth)), 3)
-        kern = sum(kern_ms) / len(kern_ms)
-
-        # ---- e2e: host rays -> H2D -> kernel -> D2H, through the host-buffer call ------------------
-        hfr = backend.HostFrameRenderer(N_RAYS, dev)
-        for i in range(min(args.warmup, 2)):
-            hfr.render(rays_host[i % n_distinct], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD), N_samples=S,
-                       mlp_mode=mode)
-        barrier()
-        e2e_steps = args.steps
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            hfr.render(rays_host[(args.warmup + i) % n_distinct], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD),
-                       N_samples=S, mlp_mode=mode)
-            if world > 1:
-                dist.barrier()
-        barrier()
-        e2e_t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        # per-rank trace of the step's two parts (what a scaling loss would have to come from)
+        trace = None
         if world > 1:
-            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        e2e_value = world * N_RAYS * e2e_steps / float(e2e_t.item())
+            mine = torch.tensor([_median(kern_list), max(kern_list), _median(rest_list), max(rest_list)], device=dev,
+                                dtype=torch.float64)
+            allr = torch.empty(world, 4, device=dev, dtype=torch.float64)
+            dist.all_gather_into_tensor(allr, mine)
+            trace = {"render_ms_median_per_rank": [round(float(x), 4) for x in allr[:, 0]],
+                     "render_ms_max_per_rank": [round(float(x), 4) for x in allr[:, 1]],
+                     "assembly_ms_median_per_rank": [round(float(x), 4) for x in allr[:, 2]],
+                     "assembly_ms_max_per_rank": [round(float(x), 4) for x in allr[:, 3]],
+                     "note": "CUDA events per step on each rank: render = the kernel launch (with its peer stores), "
+                             "assembly = what follows it inside the step (peer: 1-element barrier; nccl: pack + all-gather), "
+                             "including the wait for the slowest rank"}
 
-        # parity of this mode against the fp32 CUDA kernel on the last frame (the oracle-gated reference, tests/)
+        # ---- e2e: host rays -> H2D -> kernel -> (assembly) -> D2H, through the host-buffer call ---------
+        def e2e_run(m, n_steps):
+            hfr = backend.HostFrameRenderer(N_RAYS, dev)
+
+            def one(i):
+                if assemble == "peer":
+                    hfr.render(rays_host[i % n_distinct], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD),
+                               N_samples=S, mlp_mode=m, sink=frame.sink(rank * N_RAYS), after_launch=frame.complete)
+                    frame.rotate()
+                elif assemble == "nccl":
+                    def gather():
+                        px_local[:, :3].copy_(hfr.rgb_dev); px_local[:, 3].copy_(hfr.depth_dev)
+                        dist.all_gather_into_tensor(px_all, px_local)
+                    hfr.render(rays_host[i % n_distinct], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD),
+                               N_samples=S, mlp_mode=m, after_launch=gather)
+                else:
+                    hfr.render(rays_host[i % n_distinct], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD),
+                               N_samples=S, mlp_mode=m)
+            for i in range(2):
+                one(i)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(n_steps):
+                one(args.warmup + i)
+            barrier()
+            t = max_over_ranks(time.perf_counter() - t0)
+            return world * N_RAYS * n_steps / t, hfr
+        e2e_value, hfr = e2e_run(mode, args.steps)
+
+        # ---- strong scaling (BASELINE configs 2 and 4 as ONE job): one frame / one 4096-ray batch sharded over the
+        # ranks through the shipped API (distributed.render_rays_sharded), bit-equal to the single-GPU result ----
+        strong = {}
+        frame_rays = synthetic.scene_rays(sc, path[0]).to(dev)                     # the same camera on every rank
+        c4_idx = torch.randperm(N_RAYS, generator=torch.Generator().manual_seed(4))[:4096].to(dev)
+        for name, rays_job in (("frame_512x640", frame_rays), ("c4_batch_4096_rays", frame_rays[c4_idx].contiguous())):
+            n_job = rays_job.shape[0]
+            job_frame = None
+            if assemble == "peer":
+                job_frame = mdist.PeerFrame(n_job, n_buffers=1)
+            fn_band = (lambda r, sink=None: render(r, sink=sink))
+            run = lambda: mdist.render_rays_sharded(rays_job, fn_band, frame=job_frame)
+            for _ in range(3):
+                run()
+            barrier()
+            reps = 10
+            tot = 0.0
+            for _ in range(reps):
+                flush.zero_()
+                a, b = ev(), ev()
+                a.record(); out_rgb, out_depth = run(); b.record(); b.synchronize()
+                tot += a.elapsed_time(b)
+            ms = max_over_ranks(tot) / reps
+            single_rgb, single_depth = render(rays_job)                             # this rank alone, whole job
+            same = bool(torch.equal(out_rgb, single_rgb) and torch.equal(out_depth, single_depth))
+            same = max_over_ranks(0.0 if same else 1.0) == 0.0
+            strong[name] = {"value": n_job / (ms * 1e-3), "unit": "rays/s", "ms": ms, "rays": n_job,
+                            "rays_per_gpu": n_job // world, "bit_equal_to_single_gpu": same}
+            if job_frame is not None:
+                job_frame.close()
+        strong["api"] = "mvsnerf_b200.distributed.render_rays_sharded (" + \
+            {"peer": "PeerFrame: kernel-epilogue NVLink peer stores + 1-element barrier",
+             "nccl": "one NCCL all_gather_into_tensor of packed [n,4] pixels", "none": "single process"}[assemble] + ")"
+
+        # ---- the other arithmetic tiers on the same workload (rank 0 reports; every rank runs the steps) ----------
         other = {}
-        if rank == 0 and mode != lib.MLP_FP32:
-            r32 = torch.empty_like(rgb); d32 = torch.empty_like(depth)
-            t32 = min(ev_time(lambda: backend.render_rays(rays_dev[-1], vol, d.imgs_raw, d.pose_source, fn, sc.near_far,
-                                                          float(PAD), N_samples=S, mlp_mode=lib.MLP_FP32, out=(r32, d32)), 2))
-            backend.render_rays(rays_dev[-1], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD), N_samples=S,
-                                mlp_mode=mode, out=(rgb, depth))
-            err = (rgb - r32).abs()
-            other = {"fp32_mode": {"value": N_RAYS / (t32 * 1e-3), "unit": "rays/s", "ms_per_frame": t32,
-                                   "note": "MVSN_MLP_FP32 kernel (FFMA), the 1e-4 parity mode"},
-                     "parity_vs_fp32_kernel": {"rgb_linf": float(err.max()), "rgb_mse": float((err ** 2).mean()),
-                                               "gate": 5e-3 if mode == lib.MLP_TC_HALF else 1e-4}}
-            if mode == lib.MLP_TC_HALF:            # also report the fp32-grade tensor-core mode on the same frame
-                rs = torch.empty_like(rgb); ds = torch.empty_like(depth)
-                ts = min(ev_time(lambda: backend.render_rays(rays_dev[-1], vol, d.imgs_raw, d.pose_source, fn, sc.near_far,
-                                                             float(PAD), N_samples=S, mlp_mode=lib.MLP_TC_SPLIT, out=(rs, ds)), 3))
-                es = (rs - r32).abs()
-                other["fp32_grade_tensor_mode"] = {
-                    "value": N_RAYS / (ts * 1e-3), "unit": "rays/s", "ms_per_frame": ts,
-                    "rgb_linf_vs_fp32_kernel": float(es.max()), "gate": 1e-4,
-                    "executed_tensor_TFLOPs": 3 * N_RAYS * FLOP_PER_RAY / (ts * 1e-3) / 1e12,
-                    "note": "MVSN_MLP_TC_SPLIT: 2-term fp16 operand split, 3 tcgen05 MMAs per K-step, fp32 accumulate"}
+        r32 = torch.empty_like(rgb); d32 = torch.empty_like(depth)
+        rm = torch.empty_like(rgb); dm = torch.empty_like(depth)
+        if rank == 0:
+            t32 = min(ev_time(lambda: render(rays_dev[-1], lib.MLP_FP32, out=(r32, d32)), 2))
+            render(rays_dev[-1], mode, out=(rm, dm))
+            err = (rm - r32).abs()
+            other["fp32_mode"] = {"value": N_RAYS / (t32 * 1e-3), "unit": "rays/s", "ms_per_frame": t32,
+                                  "note": "MVSN_MLP_FP32 kernel (FFMA), the oracle-gated 1e-4 parity kernel"}
+            other["parity_vs_fp32_kernel"] = {"rgb_linf": float(err.max()), "rgb_mse": float((err ** 2).mean()),
+                                              "depth_linf": float((dm - d32).abs().max()),
+                                              "gate": 5e-3 if args.mode in ("half", "pair") else 1e-4}
+        if args.mode != "split" and not args.no_fp32_tier:
+            # fp32 tier (north star: 1e-4 RGB Linf): MVSN_MLP_TC_SPLIT measured with the same rigour as the headline
+            ms_s, kern_s, _ = timed_steps(lib.MLP_TC_SPLIT, 3, args.steps)
+            e2e_s, _ = e2e_run(lib.MLP_TC_SPLIT, args.steps)
+            if rank == 0:
+                render(rays_dev[-1], lib.MLP_TC_SPLIT, out=(rm, dm))
+                ks = sum(kern_s) / len(kern_s)
+                tf = N_RAYS * FLOP_PER_RAY / (ks * 1e-3) / 1e12
+                other["fp32_tier"] = {
+                    "mlp_mode": "split", "dtype": MODE_DTYPE["split"], "value": world * N_RAYS / (ms_s * 1e-3),
+                    "unit": "rays/s", "ms_per_step": ms_s,
+                    "e2e": {"value": e2e_s, "unit": "rays/s", "h2d_bytes_per_step": hfr.h2d_bytes * world,
+                            "d2h_bytes_per_step": hfr.d2h_bytes * world},
+                    "roofline": {"bound": "tensor", "achieved": tf, "executed": 3 * tf, "peak": pk["bf16_tflops"],
+                                 "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"], "executed_frac": 3 * tf / pk["bf16_tflops"],
+                                 "kernel": MODE_KERNEL["split"], "kernel_ms": ks,
+                                 "note": "algorithmic FLOPs; the 2-term split executes 3 MMAs per K-step"},
+                    "rgb_linf_vs_fp32_kernel": float((rm - r32).abs().max()), "gate": 1e-4,
+                    "note": "MVSN_MLP_TC_SPLIT, the DEFAULT mode of backend.rendering / render_rays"}
+
+        # ---- the north star's '>= 10x' denominator, measured in THIS run: the reference's PyTorch modules on this GPU ----
+        ref_gpu = None
+        if rank == 0 and world == 1 and not args.no_torch_gpu:
+            ref_gpu = torch_gpu_reference(dev, vol, d, sc, rays_dev[-1])
 
     if rank == 0:
         tflops = N_RAYS * FLOP_PER_RAY / (kern * 1e-3) / 1e12
@@ -331,45 +460,58 @@ def run_ours(args):
         pj = os.path.join(ROOT, "profiles", "render_kernel_ncu.json")
         if os.path.exists(pj):
             prof = json.load(open(pj)).get(args.mode, {})
+        par = "single GPU"
+        if world > 1:
+            par = (f"ray-sharded x{world}, volume replicated; frame assembly: " +
+                   ("NVLink peer stores from the kernel epilogue into every rank's [n,4] frame + 1-element barrier per step"
+                    if assemble == "peer" else "one NCCL all-gather of packed [n,4] pixels per step"))
         line = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"fp32": "fp32", "half": "fp16 operands / fp32 accumulate",
-                                           "split": "2x fp16 split operands / fp32 accumulate"}[args.mode],
-            "data": "synthetic",
+            "vs_baseline": None, "dtype": MODE_DTYPE[args.mode], "data": "synthetic",
             "config": {"workload": "DTU-shaped 512x640 frame per GPU per step (configs[1]): 3 source views, pad 24, "
                                    "D=128 volume 8x128x176x208 resident, N_samples=128, ckpt mvsnerf-v0 weights",
-                       "rays_per_gpu_per_step": N_RAYS, "mlp_mode": args.mode,
-                       "parallelism": f"ray-sharded x{world}, volume replicated, all-gather of rgb+depth per step"
-                                      if world > 1 else "single GPU",
+                       "rays_per_gpu_per_step": N_RAYS, "mlp_mode": args.mode, "parallelism": par,
                        "l2": "flushed between timed steps (256 MiB write) and inputs (150 MB volume) exceed L2"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": hfr.h2d_bytes * world,
-                    "d2h_bytes_per_step": hfr.d2h_bytes * world, "steps": e2e_steps,
-                    "api": "mvsnerf_b200.backend.HostFrameRenderer.render -> mvsn_render_rays (C ABI)"},
+                    "d2h_bytes_per_step": hfr.d2h_bytes * world, "steps": args.steps,
+                    "api": "mvsnerf_b200.backend.HostFrameRenderer.render -> mvsn_render_rays[_to_peers] (C ABI)"
+                           + ("; frame assembly inside the loop" if world > 1 else "")},
             "gpu_launches": n_launch,
             "roofline": {"bound": "tensor", "achieved": tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": tflops / pk["bf16_tflops"], "traffic": prof.get("dram_bytes_per_launch"),
-                         "kernel": prof.get("kernel", "render kernel"), "kernel_ms": kern, "peak_source": pk["source"],
+                         "traffic_source": prof.get("source"),
+                         "kernel": MODE_KERNEL[args.mode], "kernel_ms": kern, "peak_source": pk["source"],
+                         "frac_of_sustained_peak": tflops / pk["bf16_tflops_sustained"],
                          "hbm_gather_GBs": gbs, "hbm_frac": gbs / pk["hbm_gbs"],
-                         "note": "algorithmic MLP FLOPs (32 178 176 / ray) over the CUDA-event kernel time, vs the "
-                                 "measured cuBLAS bf16 burst peak; hbm_* is the 51 248 B/ray gather definition"},
+                         "note": "algorithmic MLP FLOPs (32 178 176 / ray) over the render kernel's CUDA-event time on "
+                                 "the timed steps' own launches, vs the measured cuBLAS bf16 burst peak; hbm_* is the "
+                                 "51 248 B/ray gather definition (the kernel is tensor-bound, SURVEY 8(d))"},
             "volume_build": {"ms": t_build, "featurenet_ms": t_feat, "cost_volume_ms": t_cost, "costreg_ms": t_reg,
                              "cost_volume_GBs": (176.0 * nvox + 8.6e6) / (t_cost * 1e-3) / 1e9,
                              "cost_volume_hbm_frac": (176.0 * nvox + 8.6e6) / (t_cost * 1e-3) / 1e9 / pk["hbm_gbs"],
                              "costreg_TFLOPs": 111.3e9 / (t_reg * 1e-3) / 1e12,
                              "note": "once per scene (K-F FeatureNet + K-A cost volume + K-B CostRegNet, all hand-written kernels), "
                                      "not inside the step"},
+            "strong_scaling": strong,
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }
+        if trace:
+            line["step_trace"] = trace
+        if why:
+            line["config"]["peer_store_fallback"] = why
         line.update(other)
-        tg = os.path.join(ROOT, "profiles", "r01_torch_gpu_baseline_and_fullsize_parity.json")
-        if os.path.exists(tg):                              # recorded by tests/test_gpu_fullsize_oracle.py, not re-timed here
-            rec = json.load(open(tg))
-            line["reference_pytorch_gpu"] = {
-                "value": rec["render_torch_gpu_rays_per_s"], "tf32_value": rec["render_torch_gpu_tf32_rays_per_s"],
-                "unit": "rays/s", "volume_build_ms": rec["volume_build_torch_gpu_ms"],
-                "note": "the oracle's PyTorch modules on one B200 (fp32, 5120-ray chunks), recorded by "
-                        "tests/test_gpu_fullsize_oracle.py into profiles/; the north star's >=10x denominator"}
+        if ref_gpu:
+            line["reference_pytorch_gpu"] = ref_gpu
+            for k in ("value", "tf32_value"):
+                line["reference_pytorch_gpu"][f"speedup_{k}_{args.mode}"] = value / ref_gpu[k]
+                if "fp32_tier" in other:
+                    line["reference_pytorch_gpu"][f"speedup_{k}_fp32_tier"] = other["fp32_tier"]["value"] / ref_gpu[k]
+        if world == 1 and not args.no_finetune:
+            try:
+                line["finetune_step"] = finetune_step_bench(dev)
+            except Exception as e:                                  # reported, never fatal for the headline
+                line["finetune_step"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu_baseline:
             orc, _, weights, sc_cpu = cpu_reference_setup()
             sample = args.cpu_sample
@@ -382,8 +524,47 @@ def run_ours(args):
                                     "sample": f"{sample} random rays of one frame x 128 samples ({dt:.1f} s), oracle "
                                               f"port of the reference path, torch CPU, best of several pool sizes"}
         print(json.dumps(line))
+    if frame is not None:
+        frame.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def torch_gpu_reference(dev, vol, d, sc, rays):
+    """The reference's own PyTorch path on this GPU (oracle modules on cuda, fp32, 5120-ray chunks as the notebooks use),
+    one full 512x640 frame, with TF32 matmuls off (torch 2.x default) and on (torch-1.10's default, README.md:16)."""
+    from oracle import mvsnerf_oracle as orc
+    w = {k: v.to(dev) for k, v in orc.load_weights_npz(WEIGHTS).items()}
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    out = {"unit": "rays/s", "rays": N_RAYS, "chunk": 5120}
+    try:
+        for key, tf32 in (("value", False), ("tf32_value", True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.no_grad():
+                orc.render_rays(rays[:10240], vol, d.imgs_raw, d.pose_source, w, H, W, sc.near_far, float(PAD), n_samples=S,
+                                chunk=5120)
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                orc.render_rays(rays, vol, d.imgs_raw, d.pose_source, w, H, W, sc.near_far, float(PAD), n_samples=S, chunk=5120)
+                b.record(); b.synchronize()
+            out[key] = N_RAYS / (a.elapsed_time(b) * 1e-3)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    out["note"] = ("oracle restatement of the reference's PyTorch modules on this B200 (library kernels: cuBLAS/cuDNN/"
+                   "grid_sample), one full frame, measured in this run; the north star's >=10x denominator")
+    return out
+
+
+def finetune_step_bench(dev):
+    """BASELINE config 3 shape: one fine-tuning step = 1024 rays x 128 samples against an 8x128x200x200 RefVolume
+    (800x800 Blender-shaped, pad 0, white_bkgd), forward + backward + Adam on MLP and volume
+    (train_mvs_nerf_finetuning_pl.py:140-189), through backend.rendering under autograd."""
+    from mvsnerf_b200 import backend, synthetic
+    if not hasattr(backend, "finetune_step_timing"):
+        return {"error": "backend.finetune_step_timing not available in this build"}
+    return backend.finetune_step_timing(dev, WEIGHTS)
 
 
 def main():
@@ -392,9 +573,17 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("MVSN_BENCH_MODE", "half"), choices=["fp32", "half", "split"])
+    ap.add_argument("--mode", default=os.environ.get("MVSN_BENCH_MODE", "pair"), choices=["fp32", "half", "split", "pair"],
+                    help="MLP arithmetic of the headline: pair = tcgen05 CTA-pair kernel (5e-3 tier, default); "
+                         "split = fp32-grade tensor mode (also always reported as fp32_tier); half = round-1 kernel")
+    ap.add_argument("--assemble", default=os.environ.get("MVSN_BENCH_ASSEMBLE", "peer"), choices=["peer", "nccl"],
+                    help="N > 1: kernel-epilogue NVLink peer stores (falls back to nccl when peers cannot be mapped) or "
+                         "one NCCL all-gather per step")
     ap.add_argument("--cpu-sample", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32-tier", action="store_true")
+    ap.add_argument("--no-torch-gpu", action="store_true")
+    ap.add_argument("--no-finetune", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

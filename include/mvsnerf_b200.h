@@ -48,6 +48,7 @@ extern "C" {
 #define MVSN_N_COSTREG_TENSORS 30 /* 10 x (conv weight, bn gamma, bn beta), models.py:725-769          */
 #define MVSN_N_FEATURENET_TENSORS 26 /* 8 x (conv weight, bn gamma, bn beta) + toplayer (weight, bias)   */
 #define MVSN_VOL_CH          8
+#define MVSN_MAX_PEERS       16 /* ranks of one NVLink domain a frame sink can address              */
 #define MVSN_COST_CH         41
 #define MVSN_FEAT_CH         32
 
@@ -125,6 +126,35 @@ int mvsn_render_rays(const mvsn_render_scene* scene, const mvsn_ray_params* rp,
                      const float* rays, const float* t_steps, int N, int S,
                      float* rgb, float* depth, float* weights, float* alpha, float* input_feat,
                      void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU frame assembly (replaces: nothing in the reference -- its DDP flag is dead code, SURVEY.md 2.3;
+ * this is the north star's "rays shard across the GPUs of one box, the rendered image is gathered at the end",
+ * SURVEY.md 8(e), done from the render kernel's epilogue instead of by a gather pass).
+ *
+ * A frame is [n_pixels][4] fp32 texels (r, g, b, depth).  Every rank owns one copy, allocated with
+ * mvsn_peer_buffer_create (the ONE place this library allocates: the memory must be exportable to the other
+ * processes), exports its 64-byte handle, and maps the other ranks' copies with mvsn_peer_buffer_open.
+ * mvsn_render_rays_to_peers then renders this rank's band of rays and stores each finished pixel into all
+ * `n_peers` copies (NVLink peer stores, 16 bytes per pixel per peer).  The frame is complete on every rank once
+ * every rank's launch has completed (the caller orders that with any stream-level barrier).
+ * rgb / depth may be NULL here (the sink is then the only output).
+ * ------------------------------------------------------------------------------------- */
+#define MVSN_PEER_HANDLE_BYTES 64
+int mvsn_peer_buffer_create(size_t bytes, void** dev_ptr, unsigned char handle_host[MVSN_PEER_HANDLE_BYTES]);
+int mvsn_peer_buffer_open(const unsigned char handle_host[MVSN_PEER_HANDLE_BYTES], void** peer_ptr);
+int mvsn_peer_buffer_close(void* peer_ptr);
+int mvsn_peer_buffer_destroy(void* dev_ptr);
+
+typedef struct mvsn_peer_sink {
+    float* frame[MVSN_MAX_PEERS]; /* frame[r]: rank r's copy, [n_pixels,4] fp32, 16-byte aligned (own or peer-mapped) */
+    int n_peers;
+    long long first_pixel;        /* index in the frame of this call's ray 0                                       */
+} mvsn_peer_sink;
+
+int mvsn_render_rays_to_peers(const mvsn_render_scene* scene, const mvsn_ray_params* rp,
+                              const float* rays, const float* t_steps, int N, int S,
+                              const mvsn_peer_sink* sink, float* rgb, float* depth, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Cost volume  (replaces: MVSNet.build_volume_costvar_img, models.py:839-893, with

@@ -568,13 +568,17 @@ _tsteps = {}
 
 
 def render_rays(rays, volume_feature, imgs, pose_ref, network_fn, near_far, pad, N_samples=128,
-                white_bkgd=False, lindisp=False, mlp_mode=None, out=None):
+                white_bkgd=False, lindisp=False, mlp_mode=None, out=None, sink=None):
     """Fused-caller entry: one launch renders all `rays` [N,8] = (o, d, near, far).
 
     Replaces the notebooks' per-chunk loop `ray_marcher -> get_ndc_coordinate -> rendering`
     (renderer_video.ipynb "DTU video rendering"; data/ray_utils.py:152-197, utils.py:112-146) with
     perturb = 0.  `near_far` / `pad` are the arguments the reference passes to get_ndc_coordinate
-    (near_far of the source views, pad * imgScale_test).  Returns (rgb [N,3], depth [N])."""
+    (near_far of the source views, pad * imgScale_test).  Returns (rgb [N,3], depth [N]).
+
+    `sink` (a lib.PeerSink from distributed.PeerFrame.sink): the kernel epilogue additionally stores every pixel
+    as (r, g, b, depth) into all ranks' copies of the assembled frame (mvsn_render_rays_to_peers); with a sink and
+    no `out`, nothing else is written and (None, None) is returned."""
     lib = _lib.load()
     mode = DEFAULT_MLP_MODE if mlp_mode is None else mlp_mode
     rays = _lib.dev_f32(rays, "rays")
@@ -586,15 +590,22 @@ def render_rays(rays, volume_feature, imgs, pose_ref, network_fn, near_far, pad,
         _tsteps[tk] = torch.linspace(0, 1, S, device=dev)          # data/ray_utils.py:175
     sc, keep = _make_scene(pose_ref, volume_feature, imgs, network_fn, white_bkgd, mode)
     rp = _lib.RayParams(float(near_far[0]), float(near_far[1]), float(pad), int(bool(lindisp)))
-    if out is None:
+    if out is not None:
+        rgb, depth = out
+    elif sink is not None:
+        rgb = depth = None
+    else:
         rgb = torch.empty(N, 3, dtype=torch.float32, device=dev)
         depth = torch.empty(N, dtype=torch.float32, device=dev)
-    else:
-        rgb, depth = out
     with torch.cuda.device(dev):
-        _lib.check(lib.mvsn_render_rays(C.byref(sc), C.byref(rp), _lib.ptr(rays), _lib.ptr(_tsteps[tk]), N, S,
-                                        _lib.ptr(rgb), _lib.ptr(depth), None, None, None, _lib.stream_ptr()),
-                   "mvsn_render_rays")
+        if sink is not None:
+            _lib.check(lib.mvsn_render_rays_to_peers(C.byref(sc), C.byref(rp), _lib.ptr(rays), _lib.ptr(_tsteps[tk]), N, S,
+                                                     C.byref(sink), _lib.ptr(rgb), _lib.ptr(depth), _lib.stream_ptr()),
+                       "mvsn_render_rays_to_peers")
+        else:
+            _lib.check(lib.mvsn_render_rays(C.byref(sc), C.byref(rp), _lib.ptr(rays), _lib.ptr(_tsteps[tk]), N, S,
+                                            _lib.ptr(rgb), _lib.ptr(depth), None, None, None, _lib.stream_ptr()),
+                       "mvsn_render_rays")
     del keep
     return rgb, depth
 
@@ -615,12 +626,16 @@ class HostFrameRenderer:
         self.h2d_bytes = self.n * 8 * 4
         self.d2h_bytes = self.n * 4 * 4
 
-    def render(self, rays_host, volume_feature, imgs, pose_ref, network_fn, near_far, pad, **kw):
+    def render(self, rays_host, volume_feature, imgs, pose_ref, network_fn, near_far, pad, after_launch=None, **kw):
+        """`after_launch`: optional callable enqueued between the launch and the read-back (multi-GPU frame assembly:
+        distributed.PeerFrame.complete, or an all-gather); `sink=` is forwarded to render_rays."""
         if rays_host.is_cuda or tuple(rays_host.shape) != (self.n, 8):
             raise RuntimeError(f"HostFrameRenderer: expected a host tensor [{self.n}, 8]")
         self.rays_dev.copy_(rays_host, non_blocking=True)
         render_rays(self.rays_dev, volume_feature, imgs, pose_ref, network_fn, near_far, pad,
                     out=(self.rgb_dev, self.depth_dev), **kw)
+        if after_launch is not None:
+            after_launch()
         self.rgb_host.copy_(self.rgb_dev, non_blocking=True)
         self.depth_host.copy_(self.depth_dev, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()

@@ -227,16 +227,16 @@ int mvsn_render_samples(const mvsn_render_scene* scene, const float* rays_pts, c
     return dispatch_render(scene, sc, io, false, (cudaStream_t)stream);
 }
 
-int mvsn_render_rays(const mvsn_render_scene* scene, const mvsn_ray_params* rp, const float* rays,
-                     const float* t_steps, int N, int S, float* rgb, float* depth, float* weights,
-                     float* alpha, float* input_feat, void* stream) {
+static int render_rays_impl(const mvsn_render_scene* scene, const mvsn_ray_params* rp, const float* rays,
+                            const float* t_steps, int N, int S, float* rgb, float* depth, float* weights,
+                            float* alpha, float* input_feat, const mvsn_peer_sink* sink, void* stream) {
     SceneDev sc;
     int rc = make_scene(scene, sc);
     if (rc) return rc;
     MVSN_REQUIRE(rp != nullptr, MVSN_ENULL, "mvsn_render_rays: ray params NULL");
     MVSN_REQUIRE(N >= 0 && S > 0, MVSN_EBADSHAPE, "mvsn_render_rays: N=%d S=%d", N, S);
     if (N == 0) return MVSN_OK;
-    MVSN_REQUIRE(rays && t_steps && rgb && depth, MVSN_ENULL, "mvsn_render_rays: NULL required pointer");
+    MVSN_REQUIRE(rays && t_steps && (sink || (rgb && depth)), MVSN_ENULL, "mvsn_render_rays: NULL required pointer");
     MVSN_REQUIRE(aligned16(rays), MVSN_EALIGN, "rays must be 16-byte aligned");
     MVSN_REQUIRE(!input_feat || aligned16(input_feat), MVSN_EALIGN, "input_feat must be 16-byte aligned");
     RenderIO io{};
@@ -253,7 +253,68 @@ int mvsn_render_rays(const mvsn_render_scene* scene, const mvsn_ray_params* rp, 
     io.rg.hf = (float)scene->H / 4.0f;
     io.rg.lindisp = rp->lindisp;
     io.trace = g_trace;
+    if (sink) {
+        MVSN_REQUIRE(sink->n_peers >= 1 && sink->n_peers <= MVSN_MAX_PEERS, MVSN_EBADSHAPE,
+                     "peer sink: n_peers=%d (1..%d)", sink->n_peers, MVSN_MAX_PEERS);
+        MVSN_REQUIRE(sink->first_pixel >= 0, MVSN_EBADSHAPE, "peer sink: first_pixel < 0");
+        for (int p = 0; p < sink->n_peers; ++p) {
+            MVSN_REQUIRE(sink->frame[p] != nullptr, MVSN_ENULL, "peer sink: frame[%d] is NULL", p);
+            MVSN_REQUIRE(aligned16(sink->frame[p]), MVSN_EALIGN, "peer sink: frame[%d] must be 16-byte aligned", p);
+            io.sink[p] = reinterpret_cast<float4*>(sink->frame[p]);
+        }
+        io.n_sink = sink->n_peers;
+        io.sink_first = sink->first_pixel;
+    }
     return dispatch_render(scene, sc, io, true, (cudaStream_t)stream);
+}
+
+int mvsn_render_rays(const mvsn_render_scene* scene, const mvsn_ray_params* rp, const float* rays,
+                     const float* t_steps, int N, int S, float* rgb, float* depth, float* weights,
+                     float* alpha, float* input_feat, void* stream) {
+    return render_rays_impl(scene, rp, rays, t_steps, N, S, rgb, depth, weights, alpha, input_feat, nullptr, stream);
+}
+
+int mvsn_render_rays_to_peers(const mvsn_render_scene* scene, const mvsn_ray_params* rp, const float* rays,
+                              const float* t_steps, int N, int S, const mvsn_peer_sink* sink, float* rgb,
+                              float* depth, void* stream) {
+    MVSN_REQUIRE(sink != nullptr, MVSN_ENULL, "mvsn_render_rays_to_peers: sink is NULL");
+    return render_rays_impl(scene, rp, rays, t_steps, N, S, rgb, depth, nullptr, nullptr, nullptr, sink, stream);
+}
+
+// ---- exportable frame buffers (CUDA IPC): the one allocation this library makes --------------------------
+int mvsn_peer_buffer_create(size_t bytes, void** dev_ptr, unsigned char* handle_host) {
+    MVSN_REQUIRE(dev_ptr && handle_host && bytes > 0, MVSN_ENULL, "mvsn_peer_buffer_create: bad argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == MVSN_PEER_HANDLE_BYTES, "IPC handle size");
+    void* p = nullptr;
+    MVSN_CUDA_CHECK(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+        return MVSN_ECUDA;
+    }
+    memcpy(handle_host, &h, sizeof(h));
+    *dev_ptr = p;
+    return MVSN_OK;
+}
+
+int mvsn_peer_buffer_open(const unsigned char* handle_host, void** peer_ptr) {
+    MVSN_REQUIRE(handle_host && peer_ptr, MVSN_ENULL, "mvsn_peer_buffer_open: NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_host, sizeof(h));
+    MVSN_CUDA_CHECK(cudaIpcOpenMemHandle(peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return MVSN_OK;
+}
+
+int mvsn_peer_buffer_close(void* peer_ptr) {
+    if (peer_ptr) MVSN_CUDA_CHECK(cudaIpcCloseMemHandle(peer_ptr));
+    return MVSN_OK;
+}
+
+int mvsn_peer_buffer_destroy(void* dev_ptr) {
+    if (dev_ptr) MVSN_CUDA_CHECK(cudaFree(dev_ptr));
+    return MVSN_OK;
 }
 
 }  // extern "C"

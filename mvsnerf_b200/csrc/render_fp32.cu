@@ -334,8 +334,7 @@ render_fp32_kernel(const SceneDev sc, const RenderIO io, const float* __restrict
                 } else {
                     const int ray = grp * R + tid;
                     if (sc.white_bkgd) { const float bg = 1.f - ac; cr += bg; cg += bg; cb += bg; }
-                    io.rgb[(size_t)ray * 3 + 0] = cr; io.rgb[(size_t)ray * 3 + 1] = cg; io.rgb[(size_t)ray * 3 + 2] = cb;
-                    io.depth[ray] = dp;
+                    store_pixel(io, ray, cr, cg, cb, dp);
                 }
             }
             __syncthreads();

@@ -43,7 +43,26 @@ struct RenderIO {
     int rays_per_tile;     // tensor-core kernel: chosen by its launcher
     float* rgb; float* depth; float* weights; float* alpha; float* input_feat;
     long long* trace;      // debug timeline (mvsn_debug_set_trace), null in normal operation
+    // multi-GPU frame sink (mvsn_render_rays_to_peers): every finished pixel is stored as one 16-byte
+    // (r, g, b, depth) texel into EVERY rank's copy of the assembled frame, straight from the compositing
+    // epilogue over NVLink peer mappings -- the frame is complete on all ranks when the kernels are, with no
+    // gather pass.  n_sink == 0: off.
+    float4* sink[MVSN_MAX_PEERS];
+    int n_sink;
+    long long sink_first;  // frame index of this launch's ray 0
 };
+
+// final pixel of ray `ray`: the caller's rgb / depth arrays (either may be null when a sink is given) and the sink
+__device__ __forceinline__ void store_pixel(const RenderIO& io, int ray, float r, float g, float b, float d) {
+    if (io.rgb) { io.rgb[(size_t)ray * 3 + 0] = r; io.rgb[(size_t)ray * 3 + 1] = g; io.rgb[(size_t)ray * 3 + 2] = b; }
+    if (io.depth) io.depth[ray] = d;
+    if (io.n_sink > 0) {
+        const float4 px = make_float4(r, g, b, d);
+        const long long at = io.sink_first + ray;
+#pragma unroll 1
+        for (int p = 0; p < io.n_sink; ++p) io.sink[p][at] = px;
+    }
+}
 
 int launch_render_fp32(const SceneDev& sc, const RenderIO& io, bool fast, const float* wts, cudaStream_t stream);
 int launch_render_tc(const SceneDev& sc, const RenderIO& io, bool fast, const void* wimg, cudaStream_t stream);

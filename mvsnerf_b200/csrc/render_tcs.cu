@@ -360,8 +360,7 @@ render_tcs_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restric
                             if (tile_cur == NT - 1) {
                                 float o0 = c0, o1 = c1, o2 = c2;
                                 if (sc.white_bkgd) { const float bg = 1.f - c4; o0 += bg; o1 += bg; o2 += bg; }
-                                io.rgb[(size_t)cray * 3 + 0] = o0; io.rgb[(size_t)cray * 3 + 1] = o1; io.rgb[(size_t)cray * 3 + 2] = o2;
-                                io.depth[cray] = c3;
+                                store_pixel(io, cray, o0, o1, o2, c3);
                             }
                         }
                     }

@@ -25,7 +25,10 @@ EXPORTS = [
     "mvsn_build_cost_volume", "mvsn_costreg_workspace_bytes", "mvsn_costreg_forward",
     "mvsn_featurenet_workspace_bytes", "mvsn_featurenet_forward",
     "mvsn_selftest_umma", "mvsn_debug_set_trace",
+    "mvsn_peer_buffer_create", "mvsn_peer_buffer_open", "mvsn_peer_buffer_close", "mvsn_peer_buffer_destroy",
+    "mvsn_render_rays_to_peers",
 ]
+MAX_PEERS, PEER_HANDLE_BYTES = 16, 64
 
 
 class RenderScene(C.Structure):
@@ -33,6 +36,10 @@ class RenderScene(C.Structure):
                 ("imgs_hwc4", C.c_void_p), ("V", C.c_int), ("H", C.c_int), ("W", C.c_int),
                 ("w2cs", C.c_void_p), ("intrinsics", C.c_void_p),
                 ("mlp_packed", C.c_void_p), ("mlp_mode", C.c_int), ("white_bkgd", C.c_int)]
+
+
+class PeerSink(C.Structure):
+    _fields_ = [("frame", C.c_void_p * 16), ("n_peers", C.c_int), ("first_pixel", C.c_longlong)]
 
 
 class RayParams(C.Structure):
@@ -72,12 +79,20 @@ def load() -> C.CDLL:
     lib.mvsn_featurenet_workspace_bytes.restype = C.c_size_t
     lib.mvsn_featurenet_workspace_bytes.argtypes = [ip, ip, ip]
     lib.mvsn_featurenet_forward.argtypes = [C.POINTER(vp), vp, ip, ip, ip, vp, vp, C.c_size_t, vp]
+    lib.mvsn_render_rays_to_peers.argtypes = [C.POINTER(RenderScene), C.POINTER(RayParams), vp, vp, ip, ip,
+                                              C.POINTER(PeerSink), vp, vp, vp]
+    lib.mvsn_peer_buffer_create.argtypes = [C.c_size_t, C.POINTER(vp), C.c_char_p]
+    lib.mvsn_peer_buffer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.mvsn_peer_buffer_close.argtypes = [vp]
+    lib.mvsn_peer_buffer_destroy.argtypes = [vp]
     lib.mvsn_debug_set_trace.argtypes = [vp]
     lib.mvsn_debug_set_trace.restype = None
     lib.mvsn_selftest_umma.argtypes = [vp, vp, vp, ip, ip, vp, vp]
     for name in ("mvsn_selftest_umma", "mvsn_mlp_pack", "mvsn_pack_images", "mvsn_volume_to_channels_last",
                  "mvsn_volume_from_channels_last", "mvsn_render_samples", "mvsn_render_rays",
-                 "mvsn_build_cost_volume", "mvsn_costreg_forward", "mvsn_featurenet_forward"):
+                 "mvsn_build_cost_volume", "mvsn_costreg_forward", "mvsn_featurenet_forward",
+                 "mvsn_render_rays_to_peers", "mvsn_peer_buffer_create", "mvsn_peer_buffer_open",
+                 "mvsn_peer_buffer_close", "mvsn_peer_buffer_destroy"):
         getattr(lib, name).restype = ip
     _lib = lib
     return lib

@@ -215,3 +215,66 @@ def test_sharded_api_on_a_one_rank_nccl_group(scene):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", [lib.MLP_FP32, lib.MLP_TC_HALF, lib.MLP_TC_SPLIT, lib.MLP_TC_PAIR])
+def test_peer_sink_stores_equal_the_plain_outputs(scene, mode):
+    """mvsn_render_rays_to_peers: the (r,g,b,depth) texels the compositing epilogue stores into the frame copies
+    (two 'peers' here, both on this GPU, at a non-zero first_pixel) are bit-identical to the rgb / depth arrays,
+    pixels outside the band stay untouched, and the sink-only form (rgb = depth = NULL) writes the same frame."""
+    sc, d = scene
+    fn, mvs = backend.MVSNeRF().to(DEV), backend.MVSNet().to(DEV).train()
+    backend.load_weights_npz(fn, mvs, WPATH)
+    with torch.no_grad():
+        vol, _, _ = mvs(d.imgs_norm, d.proj_mats, sc.near_far, pad=sc.pad)
+        rays = synthetic.scene_rays(sc)[:1501].contiguous().to(DEV)
+        n, first = rays.shape[0], 37
+        frames = [torch.full((n + 100, 4), -7.0, device=DEV) for _ in range(2)]
+        sink = lib.PeerSink()
+        sink.frame[0], sink.frame[1], sink.n_peers, sink.first_pixel = frames[0].data_ptr(), frames[1].data_ptr(), 2, first
+        rgb, depth = backend.render_rays(rays, vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(sc.pad), N_samples=32,
+                                         mlp_mode=mode, out=(torch.empty(n, 3, device=DEV), torch.empty(n, device=DEV)), sink=sink)
+        plain = backend.render_rays(rays, vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(sc.pad), N_samples=32, mlp_mode=mode)
+        assert torch.equal(rgb, plain[0]) and torch.equal(depth, plain[1])
+        for f in frames:
+            assert torch.equal(f[first:first + n, :3], rgb) and torch.equal(f[first:first + n, 3], depth)
+            assert bool((f[:first] == -7.0).all()) and bool((f[first + n:] == -7.0).all())
+        only = torch.full((n + 100, 4), -7.0, device=DEV)
+        s1 = lib.PeerSink()
+        s1.frame[0], s1.n_peers, s1.first_pixel = only.data_ptr(), 1, first
+        r = backend.render_rays(rays, vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(sc.pad), N_samples=32, mlp_mode=mode, sink=s1)
+        assert r == (None, None) and torch.equal(only, frames[0])
+
+
+def test_peer_frame_single_process(scene):
+    """distributed.PeerFrame without a process group: exportable buffer, tensor view over it, render through the sink."""
+    sc, d = scene
+    fn, mvs = backend.MVSNeRF().to(DEV), backend.MVSNet().to(DEV).train()
+    backend.load_weights_npz(fn, mvs, WPATH)
+    with torch.no_grad():
+        vol, _, _ = mvs(d.imgs_norm, d.proj_mats, sc.near_far, pad=sc.pad)
+        rays = synthetic.scene_rays(sc).to(DEV)
+        frame = distributed.PeerFrame(rays.shape[0], n_buffers=2)
+        render = lambda r, sink=None: backend.render_rays(r, vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(sc.pad),
+                                                          N_samples=32, sink=sink)
+        for _ in range(3):
+            rgb, depth = distributed.render_rays_sharded(rays, render, frame=frame)
+            r2, d2 = render(rays)
+            assert torch.equal(rgb, r2) and torch.equal(depth, d2)
+            frame.rotate()
+        frame.close()
+
+
+def test_two_gpu_sharding_nccl_and_peer_stores():
+    """tools/multi_gpu_check.py under torchrun on 2 GPUs: NCCL all-gather and NVLink peer-store assembly both
+    bit-equal to the single-GPU frame in every MLP mode.  Skipped on single-GPU boxes (the driver's GPU test tier);
+    profiles/r02_multi_gpu_check_2gpu.json is the committed record of a 2-GPU run."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "multi_gpu_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
