@@ -128,6 +128,51 @@ int mvsn_render_rays(const mvsn_render_scene* scene, const mvsn_ray_params* rp,
                      void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Fine-tuning step  (replaces: autograd through renderer.rendering + torch.optim.Adam in
+ *   train_mvs_nerf_finetuning_pl.py:140-189 -- gradients of the 22 MLP tensors, models.py:145-222, and of
+ *   RefVolume.feat_volume, models.py:935-950 -- SURVEY.md 8(f) row 2).
+ *
+ * mvsn_render_backward re-evaluates the samples in fp32 and back-propagates the given output gradients in one
+ * kernel: reverse compositing scan, MLP dgrad/wgrad, trilinear scatter-add into the volume gradient.
+ *   scene->mlp_packed must be the MVSN_MLP_FP32 image (scene->mlp_mode == MVSN_MLP_FP32);
+ *   mlp_w[22]: the live nn.Linear tensors (device pointers, order as mvsn_mlp_pack);
+ *   inputs as mvsn_render_samples; N_samples <= 128;
+ *   g: output gradients.  Either g->rgb [N,3] (d loss / d rgb_map) or g->target_rgb [N,3] with g->loss_scale =
+ *      1 / (3 * N_total): the img2mse loss and its gradient are then formed in the kernel (g->loss_out, if set, is
+ *      ACCUMULATED with this call's share of the loss; g->rgb_out / g->depth_out receive the forward result).
+ *      g->depth [N], g->weights [N,S], g->alpha [N,S], g->input_feat [N,S,20] optional (NULL = zero).
+ *   grad_mlp[22]: OVERWRITTEN with d loss / d tensor, nn.Linear layouts;
+ *   grad_volume_dhwc: [D,Hp,Wp,8] channels-last, ACCUMULATED (atomics); NULL = volume frozen;
+ *   workspace: mvsn_render_backward_workspace_bytes(N, S) bytes, 16-byte aligned.
+ * mvsn_adam_step / mvsn_adam_step_volume: torch.optim.Adam arithmetic (betas, eps, bias correction by `step` >= 1,
+ *   no weight decay / amsgrad).  The volume variant reads the channels-last gradient, zeroes it for the next step,
+ *   and updates a parameter (and moments) stored channels-last (planar = 0) or planar [8][nvox] (planar = 1).
+ * ------------------------------------------------------------------------------------- */
+typedef struct mvsn_render_grads {
+    const float* rgb;
+    const float* target_rgb;
+    float loss_scale;
+    const float* depth;
+    const float* weights;
+    const float* alpha;
+    const float* input_feat;
+    float* rgb_out;
+    float* depth_out;
+    float* loss_out;
+} mvsn_render_grads;
+
+size_t mvsn_render_backward_workspace_bytes(int N, int S);
+int mvsn_render_backward(const mvsn_render_scene* scene, const float* const* mlp_w,
+                         const float* rays_pts, const float* rays_ndc, const float* z_vals, const float* rays_dir,
+                         int N, int S, const mvsn_render_grads* g, float* const* grad_mlp, float* grad_volume_dhwc,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int mvsn_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                   const int* numel_host, int count, float lr, float beta1, float beta2, float eps, int step,
+                   void* stream);
+int mvsn_adam_step_volume(float* param, float* grad_dhwc, float* exp_avg, float* exp_avg_sq, long long nvox,
+                          int planar, float lr, float beta1, float beta2, float eps, int step, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Multi-GPU frame assembly (replaces: nothing in the reference -- its DDP flag is dead code, SURVEY.md 2.3;
  * this is the north star's "rays shard across the GPUs of one box, the rendered image is gathered at the end",
  * SURVEY.md 8(e), done from the render kernel's epilogue instead of by a gather pass).
@@ -195,12 +240,30 @@ int mvsn_featurenet_forward(const float* const* w_host_array_of_device_ptrs, con
  *          Conv3d [Cout,Cin,3,3,3]; ConvTranspose3d [Cin,Cout,3,3,3].
  *   cost [41,D,Hp,Wp] -> volume_dhwc [D,Hp,Wp,8] (channels-last; use
  *   mvsn_volume_from_channels_last for the reference layout).  D, Hp, Wp must be divisible by 8.
- *   Batch statistics are always used (every shipped caller runs MVSNet.train()).
+ *   Batch statistics (every shipped caller runs MVSNet.train()); see mvsn_costreg_forward_bn for eval mode.
  * ------------------------------------------------------------------------------------- */
 size_t mvsn_costreg_workspace_bytes(int D, int Hp, int Wp);
 int mvsn_costreg_forward(const float* const* w_host_array_of_device_ptrs, const float* cost,
                          int D, int Hp, int Wp, float* volume_dhwc,
                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* BatchNorm mode of the two encoder entry points (InPlaceABN, models.py:661-685; `self.training` dispatch,
+ * SURVEY.md 8(b)):
+ *   MVSN_BN_BATCH         batch statistics, running statistics untouched (the plain entry points above);
+ *   MVSN_BN_BATCH_UPDATE  batch statistics AND the train-mode side effect of F.batch_norm: running_mean / running_var
+ *                         are updated in place with `momentum` (variance unbiased) -- what MVSNet.train()(...) does
+ *                         to the buffers save_ckpt later serialises;
+ *   MVSN_BN_RUNNING       eval mode: normalise with running_mean / running_var.
+ * running[2 L]: for each BN layer in the order of w: (running_mean, running_var); L = 8 (FeatureNet), 10 (CostRegNet). */
+#define MVSN_BN_BATCH         0
+#define MVSN_BN_BATCH_UPDATE  1
+#define MVSN_BN_RUNNING       2
+int mvsn_featurenet_forward_bn(const float* const* w_host_array_of_device_ptrs, float* const* running, int bn_mode,
+                               float momentum, const float* imgs, int V, int H, int W, float* feats,
+                               void* workspace, size_t workspace_bytes, void* stream);
+int mvsn_costreg_forward_bn(const float* const* w_host_array_of_device_ptrs, float* const* running, int bn_mode,
+                            float momentum, const float* cost, int D, int Hp, int Wp, float* volume_dhwc,
+                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Diagnostic: one 128 x N x K fp16 GEMM (fp32 accumulate) through the same tcgen05 building blocks

@@ -97,11 +97,12 @@ class FeatureNet(nn.Module):
                 out += [m.conv.weight, m.bn.weight, m.bn.bias]
         return out + [self.toplayer.weight, self.toplayer.bias]
 
+    def bn_modules(self):
+        return [m.bn for block in (self.conv0, self.conv1, self.conv2) for m in block]
+
     def forward(self, x):
-        """x [V,3,H,W] -> [V,32,ceil(H/4),ceil(W/4)]."""
-        if not self.training:
-            raise RuntimeError("FeatureNet is in eval mode: the CUDA path implements batch-statistics BN only "
-                               "(every shipped caller runs MVSNet.train(), SURVEY.md F2)")
+        """x [V,3,H,W] -> [V,32,ceil(H/4),ceil(W/4)].  BatchNorm dispatches on `self.training` like InPlaceABN
+        (models.py:661-672): train = batch statistics over the V views (+ running-statistics update), eval = running."""
         lib = _lib.load()
         x = _lib.dev_f32(x.detach(), "FeatureNet input")
         V, C, H, W = x.shape
@@ -111,10 +112,27 @@ class FeatureNet(nn.Module):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         feats = torch.empty(V, 32, (H + 3) // 4, (W + 3) // 4, dtype=torch.float32, device=x.device)
         weights = [_lib.dev_f32(w.detach(), "FeatureNet weight") for w in self.weight_list()]
+        running, mode, momentum = _bn_call_args(self.bn_modules(), self.training)
         with torch.cuda.device(x.device):
-            _lib.check(lib.mvsn_featurenet_forward(_lib.ptr_array(weights), _lib.ptr(x), V, H, W, _lib.ptr(feats),
-                                                   _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "mvsn_featurenet_forward")
+            _lib.check(lib.mvsn_featurenet_forward_bn(_lib.ptr_array(weights), _lib.ptr_array(running), mode, momentum,
+                                                      _lib.ptr(x), V, H, W, _lib.ptr(feats), _lib.ptr(ws), ws_bytes,
+                                                      _lib.stream_ptr()), "mvsn_featurenet_forward_bn")
         return feats
+
+
+def _bn_call_args(bns, training):
+    """(running-statistics pointers, MVSN_BN_* mode, momentum) for a stack of InPlaceABN parameter containers."""
+    running = []
+    for bn in bns:
+        for t in (bn.running_mean, bn.running_var):
+            if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("BatchNorm running statistics must be contiguous CUDA fp32 buffers")
+            running.append(t)
+    if not training:
+        return running, _lib.BN_RUNNING, 0.0
+    for bn in bns:
+        bn.num_batches_tracked += 1                     # as nn.BatchNorm / InPlaceABN do in train mode
+    return running, _lib.BN_BATCH_UPDATE, float(bns[0].momentum)
 
 
 class CostRegNet(nn.Module):
@@ -144,8 +162,16 @@ class CostRegNet(nn.Module):
             out += [conv.weight, bn.weight, bn.bias]
         return out
 
+    def bn_modules(self):
+        out = []
+        for name in self.LAYERS:
+            m = getattr(self, name)
+            out.append(m.bn if isinstance(m, ConvBnReLU3D) else m[1])
+        return out
+
     def forward(self, cost):
-        """cost [1,41,D,Hp,Wp] (reference layout) -> [1,8,D,Hp,Wp] (channels-last memory)."""
+        """cost [1,41,D,Hp,Wp] (reference layout) -> [1,8,D,Hp,Wp] (channels-last memory).  BatchNorm dispatches on
+        `self.training` (models.py:674-685): batch statistics (+ running update) in train mode, running in eval."""
         lib = _lib.load()
         cost = _lib.dev_f32(cost, "cost volume")
         _, _, D, Hp, Wp = cost.shape
@@ -153,9 +179,11 @@ class CostRegNet(nn.Module):
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=cost.device)
         vol = torch.empty(D, Hp, Wp, 8, dtype=torch.float32, device=cost.device)
         weights = [_lib.dev_f32(w.detach(), "CostRegNet weight") for w in self.weight_list()]
+        running, mode, momentum = _bn_call_args(self.bn_modules(), self.training)
         with torch.cuda.device(cost.device):
-            _lib.check(lib.mvsn_costreg_forward(_lib.ptr_array(weights), _lib.ptr(cost), D, Hp, Wp, _lib.ptr(vol),
-                                                _lib.ptr(ws), ws_bytes, _lib.stream_ptr()), "mvsn_costreg_forward")
+            _lib.check(lib.mvsn_costreg_forward_bn(_lib.ptr_array(weights), _lib.ptr_array(running), mode, momentum,
+                                                   _lib.ptr(cost), D, Hp, Wp, _lib.ptr(vol), _lib.ptr(ws), ws_bytes,
+                                                   _lib.stream_ptr()), "mvsn_costreg_forward_bn")
         return vol.permute(3, 0, 1, 2).unsqueeze(0)
 
 
@@ -164,7 +192,9 @@ class FrozenEncoderWarning(UserWarning):
 
 
 class MVSNet(nn.Module):
-    """Encoding-volume builder with the reference's call signature (models.py:771-932)."""
+    """Encoding-volume builder with the reference's call signature (models.py:771-932).  `.train()` / `.eval()` select
+    batch-statistics or running-statistics BatchNorm exactly as for the reference module (every shipped caller runs
+    `.train()` first; eval mode gives very different volumes with the shipped checkpoint, App. D)."""
 
     def __init__(self):
         super().__init__()
@@ -200,11 +230,6 @@ class MVSNet(nn.Module):
         return cost, masks
 
     def forward(self, imgs, proj_mats, near_far, pad=0, return_color=False, lindisp=False):
-        if not self.training:
-            raise RuntimeError(
-                "MVSNet is in eval mode: every shipped caller of the reference runs MVSNet.train() "
-                "(batch-statistics BN, SURVEY.md F2) and the CUDA path implements exactly that; "
-                "call .train() first")
         if not imgs.is_cuda:
             raise RuntimeError("MVSNet: inputs must be CUDA tensors; mvsnerf_b200 has no CPU path")
         if torch.is_grad_enabled() and (imgs.requires_grad or any(p.requires_grad for p in self.parameters())):
@@ -534,12 +559,23 @@ class _RenderSamplesFn(torch.autograd.Function):
         pose = {"w2cs": w2cs, "intrinsics": intrinsics}
         out = _render_samples_kernel(pose, pts, ndc, z, rays_dir, volume_feature, imgs, network_fn, white_bkgd, mode)
         ctx.save_for_backward(pts, ndc, z, rays_dir, vol, imgs, w2cs, intrinsics, *params)
-        ctx.white_bkgd, ctx.network_fn = white_bkgd, network_fn
+        ctx.white_bkgd, ctx.network_fn, ctx.volume_feature = white_bkgd, network_fn, volume_feature
         return out
 
     @staticmethod
     def backward(ctx, g_rgb, g_feat, g_weights, g_depth, g_alpha):
         pts, ndc, z, rays_dir, vol, imgs, w2cs, intrinsics, *params = ctx.saved_tensors
+        S = pts.shape[1]
+        if S <= 128 and BACKWARD_IMPL == "kernel":
+            # the hand-written backward kernel (csrc/render_bwd.cu): recompute + dgrad/wgrad + volume scatter
+            need_vol = ctx.needs_input_grad[4]
+            grads = {"rgb": g_rgb, "depth": g_depth, "weights": g_weights, "alpha": g_alpha, "input_feat": g_feat}
+            g_params, dvol, _, _ = render_backward(
+                {"w2cs": w2cs, "intrinsics": intrinsics}, pts, ndc, z, rays_dir, ctx.volume_feature, imgs, ctx.network_fn,
+                ctx.white_bkgd, grads=grads, want_volume_grad=need_vol)
+            g_vol = dvol.permute(3, 0, 1, 2).unsqueeze(0) if need_vol else None
+            g_params = [g if need else None for g, need in zip(g_params, ctx.needs_input_grad[12:])]
+            return (None, None, None, None, g_vol, None, None, None, None, None, None, None, *g_params)
         with torch.enable_grad():
             vol_g = vol.detach().requires_grad_(ctx.needs_input_grad[4])
             # evaluate through a functional copy of the module so the user's parameters are not touched
@@ -556,6 +592,255 @@ class _RenderSamplesFn(torch.autograd.Function):
         g_vol = next(it) if vol_g.requires_grad and grads else None
         g_params = [next(it) if (leaf.requires_grad and grads) else None for leaf in leaves]
         return (None, None, None, None, g_vol, None, None, None, None, None, None, None, *g_params)
+
+
+# "kernel": csrc/render_bwd.cu (N_samples <= 128); "torch": the PyTorch-recompute backward above (kept as the
+# independent statement the gradient tests compare against, and for N_samples > 128)
+BACKWARD_IMPL = "kernel"
+_bwd_workspace = {}
+
+
+def _backward_workspace(dev, N, S):
+    lib = _lib.load()
+    need = lib.mvsn_render_backward_workspace_bytes(int(N), int(S))
+    if need == 0:
+        raise RuntimeError(f"render backward: unsupported shape N={N}, N_samples={S} (N_samples <= 128)")
+    ws = _bwd_workspace.get(dev)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        _bwd_workspace[dev] = ws
+    return ws, need
+
+
+def render_backward(pose_ref, rays_pts, rays_ndc, z_vals, rays_dir, volume_feature, imgs, network_fn, white_bkgd=False,
+                    grads=None, target_rgb=None, n_total=None, want_volume_grad=True, grad_volume=None, grad_mlp=None,
+                    want_forward=False, loss_out=None):
+    """One mvsn_render_backward launch.  Either `grads` (dict with 'rgb' and optionally 'depth', 'weights', 'alpha',
+    'input_feat': d loss / d output of `rendering`) or `target_rgb` [N,3] (img2mse formed in the kernel, normalised by
+    3 * n_total).  Returns (grad_mlp[22] in ordered_params() order, grad_volume [D,Hp,Wp,8] channels-last or None,
+    rgb [N,3] or None, depth [N] or None).  `grad_volume` (accumulated into) and `grad_mlp` (overwritten) may be passed
+    to reuse buffers."""
+    lib = _lib.load()
+    N, S = rays_pts.shape[:2]
+    dev = rays_pts.device
+    pts = _lib.dev_f32(rays_pts.detach(), "rays_pts")
+    ndc = _lib.dev_f32(rays_ndc.detach(), "rays_ndc")
+    z = _lib.dev_f32((z_vals.expand(N, S) if z_vals.shape != (N, S) else z_vals).detach(), "depth_candidates")
+    dirs = _lib.dev_f32(rays_dir.detach(), "rays_dir")
+    sc, keep = _make_scene(pose_ref, volume_feature, imgs, network_fn, white_bkgd, _lib.MLP_FP32)
+    params = [_lib.dev_f32(p.detach(), "MLP parameter") for p in network_fn.ordered_params()]
+    if grad_mlp is None:
+        grad_mlp = [torch.empty_like(p) for p in params]
+    if want_volume_grad and grad_volume is None:
+        grad_volume = torch.zeros(sc.D, sc.Hp, sc.Wp, 8, dtype=torch.float32, device=dev)
+    g = _lib.RenderGrads()
+    held = []
+
+    def opt(t, shape, name):
+        if t is None:
+            return None
+        t = _lib.dev_f32(t.detach(), name)
+        if tuple(t.shape) != tuple(shape):
+            t = t.expand(shape).contiguous()
+        held.append(t)
+        return t.data_ptr()
+    if target_rgb is not None:
+        g.target_rgb = opt(target_rgb, (N, 3), "target_rgb")
+        g.loss_scale = 1.0 / (3.0 * float(N if n_total is None else n_total))
+    else:
+        if grads is None or grads.get("rgb") is None:
+            grads = dict(grads or {})
+            grads["rgb"] = torch.zeros(N, 3, dtype=torch.float32, device=dev)
+        g.rgb = opt(grads["rgb"], (N, 3), "grad rgb")
+    if grads is not None:
+        g.depth = opt(grads.get("depth"), (N,), "grad depth")
+        g.weights = opt(grads.get("weights"), (N, S), "grad weights")
+        g.alpha = opt(grads.get("alpha"), (N, S), "grad alpha")
+        g.input_feat = opt(grads.get("input_feat"), (N, S, 20), "grad input_feat")
+    rgb = depth = None
+    if want_forward:
+        rgb = torch.empty(N, 3, dtype=torch.float32, device=dev)
+        depth = torch.empty(N, dtype=torch.float32, device=dev)
+        g.rgb_out, g.depth_out = rgb.data_ptr(), depth.data_ptr()
+    if loss_out is not None:
+        g.loss_out = loss_out.data_ptr()
+    ws, ws_bytes = _backward_workspace(dev, N, S)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mvsn_render_backward(C.byref(sc), _lib.ptr_array(params), _lib.ptr(pts), _lib.ptr(ndc), _lib.ptr(z),
+                                            _lib.ptr(dirs), N, S, C.byref(g), _lib.ptr_array(grad_mlp),
+                                            _lib.ptr(grad_volume) if want_volume_grad else None, _lib.ptr(ws), ws_bytes,
+                                            _lib.stream_ptr()), "mvsn_render_backward")
+    del keep, held
+    return grad_mlp, (grad_volume if want_volume_grad else None), rgb, depth
+
+
+class FineTuner:
+    """The reference's per-scene fine-tuning step (train_mvs_nerf_finetuning_pl.py:140-189: rendering -> img2mse ->
+    Adam over the MLP and RefVolume.feat_volume) as four launches and no autograd graph:
+
+        mvsn_mlp_pack (fp32 image) -> mvsn_render_backward (forward recompute + loss + all gradients)
+        -> mvsn_adam_step (22 MLP tensors) -> mvsn_adam_step_volume (volume; also zeroes its gradient buffer)
+
+    The parameters stay the caller's nn.Parameters (updated in place, version counters bumped), so checkpoints, the
+    render entry points and scene_io see them as after a torch.optim.Adam step with the same hyper-parameters."""
+
+    def __init__(self, network_fn, volume, imgs, pose_ref, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, white_bkgd=False):
+        self.network_fn, self.volume, self.imgs, self.pose_ref = network_fn, volume, imgs, pose_ref
+        self.lr, self.betas, self.eps, self.white_bkgd = float(lr), (float(betas[0]), float(betas[1])), float(eps), bool(white_bkgd)
+        self.step_count = 0
+        self.params = network_fn.ordered_params()
+        dev = self.params[0].device
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+        self.g = [torch.zeros_like(p) for p in self.params]
+        fv = volume.feat_volume
+        if fv.dim() != 5 or fv.shape[0] != 1 or fv.shape[1] != 8 or not fv.is_cuda or fv.dtype != torch.float32:
+            raise RuntimeError("FineTuner: volume.feat_volume must be a CUDA fp32 tensor [1,8,D,H,W]")
+        _, _, D, Hp, Wp = fv.shape
+        self.nvox = D * Hp * Wp
+        cl = fv.detach()[0].permute(1, 2, 3, 0)
+        if cl.is_contiguous():
+            self.planar = 0                                   # channels-last storage (what MVSNet.forward returns)
+        elif fv.is_contiguous():
+            self.planar = 1                                   # checkpoint layout [8][nvox]
+        else:
+            raise RuntimeError("FineTuner: feat_volume must be contiguous either planar or channels-last")
+        self.vol_m = torch.zeros_like(fv.detach())
+        self.vol_v = torch.zeros_like(fv.detach())
+        self.vol_g = torch.zeros(D, Hp, Wp, 8, dtype=torch.float32, device=dev)   # zeroed again by every Adam step
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self._numel = (C.c_int * len(self.params))(*[p.numel() for p in self.params])
+
+    def step(self, rays_pts, rays_ndc, z_vals, rays_dir, target_rgb, lr=None, want_forward=False):
+        """One optimisation step on a batch.  Returns (loss [1] device tensor -- img2mse of this batch BEFORE the
+        update, as the reference logs it -- and (rgb, depth) of the forward pass when `want_forward`)."""
+        lib = _lib.load()
+        lr = self.lr if lr is None else float(lr)
+        self.step_count += 1
+        self.loss.zero_()
+        _, _, rgb, depth = render_backward(self.pose_ref, rays_pts, rays_ndc, z_vals, rays_dir, self.volume, self.imgs,
+                                           self.network_fn, self.white_bkgd, target_rgb=target_rgb, want_volume_grad=True,
+                                           grad_volume=self.vol_g, grad_mlp=self.g, want_forward=want_forward,
+                                           loss_out=self.loss)
+        dev = self.params[0].device
+        fv = self.volume.feat_volume
+        with torch.cuda.device(dev):
+            _lib.check(lib.mvsn_adam_step(_lib.ptr_array([p.detach() for p in self.params]), _lib.ptr_array(self.g),
+                                          _lib.ptr_array(self.m), _lib.ptr_array(self.v), self._numel, len(self.params),
+                                          lr, self.betas[0], self.betas[1], self.eps, self.step_count, _lib.stream_ptr()),
+                       "mvsn_adam_step")
+            _lib.check(lib.mvsn_adam_step_volume(_lib.ptr(fv.detach()), _lib.ptr(self.vol_g), _lib.ptr(self.vol_m),
+                                                 _lib.ptr(self.vol_v), self.nvox, self.planar, lr, self.betas[0],
+                                                 self.betas[1], self.eps, self.step_count, _lib.stream_ptr()),
+                       "mvsn_adam_step_volume")
+        # the parameters changed behind PyTorch's back: bump their version counters (weight-image / volume caches)
+        torch.autograd.graph.increment_version([p for p in self.params] + [fv])
+        return self.loss, (rgb, depth)
+
+
+def ray_marcher(rays, N_samples=64, lindisp=False, perturb=0):
+    """data/ray_utils.py:152-197 (without the bbox branch): sample points along rays [N,8] = (o, d, near, far).
+    Returns (xyz [N,S,3], rays_o [N,3], rays_d [N,3], z_vals [N,S]).  Host-side mirror for the training callers
+    (perturb > 0 draws torch.rand like the reference); inference uses the fused render_rays entry instead."""
+    n = rays.shape[0]
+    rays_o, rays_d = rays[:, 0:3], rays[:, 3:6]
+    near, far = rays[:, 6:7], rays[:, 7:8]
+    z_steps = torch.linspace(0, 1, N_samples, device=rays.device)
+    if not lindisp:
+        z_vals = near * (1 - z_steps) + far * z_steps
+    else:
+        z_vals = 1 / (1 / near * (1 - z_steps) + 1 / far * z_steps)
+    z_vals = z_vals.expand(n, N_samples)
+    if perturb > 0:
+        mid = 0.5 * (z_vals[:, :-1] + z_vals[:, 1:])
+        upper = torch.cat([mid, z_vals[:, -1:]], -1)
+        lower = torch.cat([z_vals[:, :1], mid], -1)
+        z_vals = lower + (upper - lower) * (perturb * torch.rand(z_vals.shape, device=rays.device))
+    xyz = rays_o.unsqueeze(1) + rays_d.unsqueeze(1) * z_vals.unsqueeze(2)
+    return xyz, rays_o, rays_d, z_vals
+
+
+def get_ndc_coordinate(w2c_ref, intrinsic_ref, point_samples, inv_scale, near=2, far=6, pad=0, lindisp=False):
+    """utils.py:112-146 (projection branch): world points [N,S,3] -> volume coordinates in [0,1]."""
+    n, s = point_samples.shape[:2]
+    p = point_samples.reshape(-1, 3)
+    p = torch.matmul(p, w2c_ref[:3, :3].t()) + w2c_ref[:3, 3:].reshape(1, 3)
+    q = p @ intrinsic_ref.t()
+    q[:, :2] = (q[:, :2] / q[:, -1:] + 0.0) / inv_scale.reshape(1, 2)
+    if not lindisp:
+        q[:, 2] = (q[:, 2] - near) / (far - near)
+    else:
+        q[:, 2] = (1.0 / q[:, 2] - 1.0 / near) / (1.0 / far - 1.0 / near)
+    if pad > 0:
+        w_feat, h_feat = (inv_scale + 1) / 4.0
+        q[:, 1] = q[:, 1] * h_feat / (h_feat + pad * 2) + pad / (h_feat + pad * 2)
+        q[:, 0] = q[:, 0] * w_feat / (w_feat + pad * 2) + pad / (w_feat + pad * 2)
+    return q.view(n, s, 3)
+
+
+def finetune_step_timing(dev, weights_npz, steps=20, warmup=5, batch=1024, n_samples=128):
+    """bench.py's BASELINE-config-3 entry: fine-tuning steps on a Blender-shaped scene (800x800, pad 0, white_bkgd,
+    near_far [2, 6]; encoding volume 8x128x200x200), 1024 rays x 128 samples per step, perturb = 1 -- the fused
+    FineTuner step and, beside it, the same step through `rendering` under autograd + torch.optim.Adam."""
+    from . import synthetic
+    fn, mvs = MVSNeRF().to(dev), MVSNet().to(dev).train()
+    load_weights_npz(fn, mvs, weights_npz)
+    sc = synthetic.make_scene(800, 800, pad=0, seed=3, near_far=(2.0, 6.0))
+    d = sc.to(dev)
+    with torch.no_grad():
+        vol, _, _ = mvs(d.imgs_norm, d.proj_mats, sc.near_far, pad=0)
+    rays_all = synthetic.scene_rays(sc).to(dev)
+    target_all = d.imgs_raw[0, 0].permute(1, 2, 0).reshape(-1, 3).contiguous()
+    inv_scale = torch.tensor([sc.W - 1.0, sc.H - 1.0], device=dev)
+    gen = torch.Generator(device=dev).manual_seed(0)
+
+    def batch_of():
+        idx = torch.randint(0, rays_all.shape[0], (batch,), device=dev, generator=gen)
+        rays, tgt = rays_all[idx], target_all[idx]
+        xyz, _, rays_d, z = ray_marcher(rays, N_samples=n_samples, perturb=1.0)
+        ndc = get_ndc_coordinate(d.pose_source["w2cs"][0], d.pose_source["intrinsics"][0], xyz, inv_scale,
+                                 near=sc.near_far[0], far=sc.near_far[1], pad=0)
+        return xyz, ndc, z, rays_d, tgt
+
+    def timed(fn_step):
+        for _ in range(warmup):
+            fn_step(*batch_of())
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(steps):
+            b = batch_of()
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn_step(*b); e.record(); e.synchronize()
+            ts.append(a.elapsed_time(e))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    out = {"rays": batch, "n_samples": n_samples, "volume": list(vol.shape), "white_bkgd": True}
+    volume = RefVolume(vol.detach().clone()).to(dev)
+    tuner = FineTuner(fn, volume, d.imgs_raw, d.pose_source, lr=5e-4, white_bkgd=True)
+    losses = []
+    out["fused_ms"] = timed(lambda xyz, ndc, z, rd, tgt: losses.append(tuner.step(xyz, ndc, z, rd, tgt)[0].clone()))
+    out["fused_loss_first_last"] = [float(losses[0]), float(losses[-1])]
+    # the reference's own step shape: rendering under autograd (kernel forward + kernel backward) + torch.optim.Adam
+    fn2 = MVSNeRF().to(dev)
+    load_weights_npz(fn2, None, weights_npz)
+    volume2 = RefVolume(vol.detach().clone()).to(dev)
+    opt = torch.optim.Adam(list(fn2.parameters()) + list(volume2.parameters()), lr=5e-4, betas=(0.9, 0.999))
+    from types import SimpleNamespace
+    args = SimpleNamespace(use_color_volume=False)
+
+    def autograd_step(xyz, ndc, z, rd, tgt):
+        rgb = rendering(args, d.pose_source, xyz, ndc, z, None, rd, volume2, d.imgs_raw, network_fn=fn2, white_bkgd=True,
+                        want_aux=True)[0]
+        loss = torch.mean((rgb - tgt) ** 2)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+    out["autograd_adam_ms"] = timed(autograd_step)
+    out["note"] = ("median CUDA-event ms per step incl. ray marching (torch ops) ; fused = FineTuner.step (mvsn_render_backward "
+                   "+ mvsn_adam_step + mvsn_adam_step_volume); autograd = backend.rendering under autograd (kernel backward) "
+                   "+ torch.optim.Adam; README.md's reference figure is ~15 min for 10k such steps")
+    return out
 
 
 def _ordered_named_params(network_fn):

@@ -281,6 +281,54 @@ int mvsn_render_rays_to_peers(const mvsn_render_scene* scene, const mvsn_ray_par
     return render_rays_impl(scene, rp, rays, t_steps, N, S, rgb, depth, nullptr, nullptr, nullptr, sink, stream);
 }
 
+// ---- fine-tuning step ------------------------------------------------------------------------------------
+size_t mvsn_render_backward_workspace_bytes(int N, int S) { return render_backward_workspace_bytes(N, S); }
+
+int mvsn_render_backward(const mvsn_render_scene* scene, const float* const* mlp_w, const float* rays_pts,
+                         const float* rays_ndc, const float* z_vals, const float* rays_dir, int N, int S,
+                         const mvsn_render_grads* g, float* const* grad_mlp, float* grad_volume_dhwc, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+    SceneDev sc;
+    int rc = make_scene(scene, sc);
+    if (rc) return rc;
+    MVSN_REQUIRE(scene->mlp_mode == MVSN_MLP_FP32, MVSN_EUNSUPPORTED,
+                 "mvsn_render_backward: scene->mlp_packed must be the MVSN_MLP_FP32 image (mode %d given)", scene->mlp_mode);
+    MVSN_REQUIRE(N >= 0 && S > 0, MVSN_EBADSHAPE, "mvsn_render_backward: N=%d S=%d", N, S);
+    MVSN_REQUIRE(g && mlp_w && grad_mlp, MVSN_ENULL, "mvsn_render_backward: NULL argument");
+    MVSN_REQUIRE(g->rgb || g->target_rgb, MVSN_ENULL, "mvsn_render_backward: neither g->rgb nor g->target_rgb given");
+    for (int i = 0; i < MVSN_N_MLP_TENSORS; ++i)
+        MVSN_REQUIRE(mlp_w[i] && grad_mlp[i], MVSN_ENULL, "mvsn_render_backward: tensor %d is NULL", i);
+    MVSN_REQUIRE(!grad_volume_dhwc || aligned16(grad_volume_dhwc), MVSN_EALIGN, "grad_volume_dhwc must be 16-byte aligned");
+    if (N == 0) return MVSN_OK;
+    MVSN_REQUIRE(rays_pts && rays_ndc && z_vals && rays_dir, MVSN_ENULL, "mvsn_render_backward: NULL required pointer");
+    RenderIO io{};
+    io.pts = rays_pts; io.ndc = rays_ndc; io.z = z_vals; io.dirs = rays_dir;
+    io.N = N; io.S = S;
+    return launch_render_backward(sc, io, static_cast<const float*>(scene->mlp_packed), mlp_w, g->rgb, g->target_rgb,
+                                  g->loss_scale, g->depth, g->weights, g->alpha, g->input_feat, grad_mlp,
+                                  grad_volume_dhwc, g->rgb_out, g->depth_out, g->loss_out, workspace, workspace_bytes,
+                                  (cudaStream_t)stream);
+}
+
+int mvsn_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
+                   const int* numel_host, int count, float lr, float beta1, float beta2, float eps, int step,
+                   void* stream) {
+    MVSN_REQUIRE(params && grads && exp_avg && exp_avg_sq && numel_host, MVSN_ENULL, "mvsn_adam_step: NULL argument");
+    MVSN_REQUIRE(step >= 1, MVSN_EBADSHAPE, "mvsn_adam_step: step=%d (counts from 1)", step);
+    return launch_adam_tensors(params, grads, exp_avg, exp_avg_sq, numel_host, count, lr, beta1, beta2, eps, step,
+                               (cudaStream_t)stream);
+}
+
+int mvsn_adam_step_volume(float* param, float* grad_dhwc, float* exp_avg, float* exp_avg_sq, long long nvox,
+                          int planar, float lr, float beta1, float beta2, float eps, int step, void* stream) {
+    MVSN_REQUIRE(param && grad_dhwc && exp_avg && exp_avg_sq, MVSN_ENULL, "mvsn_adam_step_volume: NULL argument");
+    MVSN_REQUIRE(nvox > 0 && step >= 1, MVSN_EBADSHAPE, "mvsn_adam_step_volume: nvox=%lld step=%d", nvox, step);
+    MVSN_REQUIRE(aligned16(grad_dhwc) && (planar || (aligned16(param) && aligned16(exp_avg) && aligned16(exp_avg_sq))),
+                 MVSN_EALIGN, "mvsn_adam_step_volume: buffers must be 16-byte aligned");
+    return launch_adam_volume(param, grad_dhwc, exp_avg, exp_avg_sq, nvox, planar, lr, beta1, beta2, eps, step,
+                              (cudaStream_t)stream);
+}
+
 // ---- exportable frame buffers (CUDA IPC): the one allocation this library makes --------------------------
 int mvsn_peer_buffer_create(size_t bytes, void** dev_ptr, unsigned char* handle_host) {
     MVSN_REQUIRE(dev_ptr && handle_host && bytes > 0, MVSN_ENULL, "mvsn_peer_buffer_create: bad argument");

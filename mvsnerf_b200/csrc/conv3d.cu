@@ -522,6 +522,18 @@ static int launch_deconv(const ConvArgs& a, cudaStream_t st) {
     return MVSN_OK;
 }
 
+__global__ void bn_update_running_kernel(const double* __restrict__ stats, double count, int C, float momentum,
+                                         float* __restrict__ rmean, float* __restrict__ rvar) {
+    const int c = threadIdx.x;
+    if (c >= C) return;
+    const double mean = stats[2 * c] / count;
+    double var = stats[2 * c + 1] / count - mean * mean;
+    var = var > 0.0 ? var : 0.0;
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    rmean[c] = (float)((1.0 - (double)momentum) * (double)rmean[c] + (double)momentum * mean);
+    rvar[c] = (float)((1.0 - (double)momentum) * (double)rvar[c] + (double)momentum * unbiased);
+}
+
 }  // namespace mvsn
 
 using namespace mvsn;
@@ -547,7 +559,17 @@ size_t mvsn_costreg_workspace_bytes(int D, int Hp, int Wp) {
 
 int mvsn_costreg_forward(const float* const* w, const float* cost, int D, int Hp, int Wp, float* volume_dhwc,
                          void* workspace, size_t workspace_bytes, void* stream_) {
+    return mvsn_costreg_forward_bn(w, nullptr, MVSN_BN_BATCH, 0.f, cost, D, Hp, Wp, volume_dhwc, workspace, workspace_bytes, stream_);
+}
+
+int mvsn_costreg_forward_bn(const float* const* w, float* const* running, int bn_mode, float momentum, const float* cost,
+                            int D, int Hp, int Wp, float* volume_dhwc, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
+    MVSN_REQUIRE(bn_mode == MVSN_BN_BATCH || bn_mode == MVSN_BN_BATCH_UPDATE || bn_mode == MVSN_BN_RUNNING, MVSN_EBADSHAPE,
+                 "mvsn_costreg_forward_bn: bn_mode %d", bn_mode);
+    MVSN_REQUIRE(bn_mode == MVSN_BN_BATCH || running, MVSN_ENULL, "mvsn_costreg_forward_bn: running statistics are NULL");
+    if (bn_mode != MVSN_BN_BATCH)
+        for (int i = 0; i < 20; ++i) MVSN_REQUIRE(running[i] != nullptr, MVSN_ENULL, "mvsn_costreg_forward_bn: running[%d] is NULL", i);
     MVSN_REQUIRE(w && cost && volume_dhwc && workspace, MVSN_ENULL, "mvsn_costreg_forward: NULL argument");
     MVSN_REQUIRE(D > 0 && Hp > 0 && Wp > 0 && D % 8 == 0 && Hp % 8 == 0 && Wp % 8 == 0, MVSN_EBADSHAPE,
                  "mvsn_costreg_forward: D=%d Hp=%d Wp=%d must all be divisible by 8 (three stride-2 levels, models.py:730-766)",
@@ -578,9 +600,11 @@ int mvsn_costreg_forward(const float* const* w, const float* cost, int D, int Hp
         ActSrc s;
         s.x = raw[l]; s.stats = stats + (size_t)l * 128; s.gamma = w[3 * l + 1]; s.beta = w[3 * l + 2];
         s.count = (double)dims[l].n();
+        s.rmean = bn_mode == MVSN_BN_RUNNING ? running[2 * l] : nullptr;
+        s.rvar = bn_mode == MVSN_BN_RUNNING ? running[2 * l + 1] : nullptr;
         return s;
     };
-    const ActSrc none{nullptr, nullptr, nullptr, nullptr, 1.0};
+    const ActSrc none{nullptr, nullptr, nullptr, nullptr, 1.0, nullptr, nullptr};
     auto args = [&](int l, ActSrc a0, ActSrc a1, Dims din) {
         ConvArgs a;
         a.in0 = a0; a.in1 = a1; a.Cin = kCin[l]; a.Din = din.D; a.Hin = din.H; a.Win = din.W;
@@ -589,7 +613,7 @@ int mvsn_costreg_forward(const float* const* w, const float* cost, int D, int Hp
         return a;
     };
     int rc;
-    ActSrc cost_src{cost, nullptr, nullptr, nullptr, 1.0};
+    ActSrc cost_src{cost, nullptr, nullptr, nullptr, 1.0, nullptr, nullptr};
     const Dims full{D, Hp, Wp};
     if ((rc = launch_conv0(args(0, cost_src, none, full), st))) return rc;                     // conv0 41->8
     if ((rc = launch_conv_auto<2>(args(1, src(0), none, dims[0]), st))) return rc;       // conv1 8->16 s2
@@ -604,6 +628,11 @@ int mvsn_costreg_forward(const float* const* w, const float* cost, int D, int Hp
     const long long nvox = full.n();
     finalize_volume_kernel<<<cdiv(nvox, 256) < sm_count() * 8 ? cdiv(nvox, 256) : sm_count() * 8, 256, 0, st>>>(
         src(0), src(9), nvox, reinterpret_cast<float4*>(volume_dhwc));
+    MVSN_CUDA_CHECK(cudaGetLastError());
+    if (bn_mode == MVSN_BN_BATCH_UPDATE)
+        for (int l = 0; l < 10; ++l)
+            bn_update_running_kernel<<<1, 64, 0, st>>>(stats + (size_t)l * 128, (double)dims[l].n(), kCout[l], momentum,
+                                                       running[2 * l], running[2 * l + 1]);
     MVSN_CUDA_CHECK(cudaGetLastError());
     return MVSN_OK;
 }

@@ -15,6 +15,8 @@ struct ActSrc {                 // one input tensor of a layer, stored raw + its
     const float* gamma;         // [C]
     const float* beta;          // [C]
     double count;
+    const float* rmean;         // eval mode: running mean / variance [C] used instead of the batch statistics
+    const float* rvar;          // (null in train mode)
 };
 
 
@@ -27,8 +29,13 @@ __device__ __forceinline__ float act(float x, float sc, float sh) {
 __device__ inline void load_norm(const ActSrc& s, int C, float* sc, float* sh, int tid, int nthreads) {
     for (int c = tid; c < C; c += nthreads) {
         if (s.stats) {
-            const double mean = s.stats[2 * c] / s.count;
-            double var = s.stats[2 * c + 1] / s.count - mean * mean;     // biased, as F.batch_norm(training=True)
+            double mean, var;
+            if (s.rmean) {                                               // F.batch_norm(training=False)
+                mean = (double)s.rmean[c]; var = (double)s.rvar[c];
+            } else {
+                mean = s.stats[2 * c] / s.count;
+                var = s.stats[2 * c + 1] / s.count - mean * mean;        // biased, as F.batch_norm(training=True)
+            }
             var = var > 0.0 ? var : 0.0;
             const double inv = 1.0 / sqrt(var + (double)kBnEps);
             const double g = fabs((double)s.gamma[c]) + (double)kBnEps;
@@ -39,5 +46,9 @@ __device__ inline void load_norm(const ActSrc& s, int C, float* sc, float* sh, i
         }
     }
 }
+
+// train mode side effect of F.batch_norm: running = (1 - momentum) running + momentum batch (variance UNBIASED, n / (n - 1))
+__global__ void bn_update_running_kernel(const double* __restrict__ stats, double count, int C, float momentum,
+                                         float* __restrict__ rmean, float* __restrict__ rvar);
 
 }  // namespace mvsn

@@ -245,7 +245,17 @@ size_t mvsn_featurenet_workspace_bytes(int V, int H, int W) {
 
 int mvsn_featurenet_forward(const float* const* w, const float* imgs, int V, int H, int W, float* feats,
                             void* workspace, size_t workspace_bytes, void* stream_) {
+    return mvsn_featurenet_forward_bn(w, nullptr, MVSN_BN_BATCH, 0.f, imgs, V, H, W, feats, workspace, workspace_bytes, stream_);
+}
+
+int mvsn_featurenet_forward_bn(const float* const* w, float* const* running, int bn_mode, float momentum, const float* imgs,
+                               int V, int H, int W, float* feats, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
+    MVSN_REQUIRE(bn_mode == MVSN_BN_BATCH || bn_mode == MVSN_BN_BATCH_UPDATE || bn_mode == MVSN_BN_RUNNING, MVSN_EBADSHAPE,
+                 "mvsn_featurenet_forward_bn: bn_mode %d", bn_mode);
+    MVSN_REQUIRE(bn_mode == MVSN_BN_BATCH || running, MVSN_ENULL, "mvsn_featurenet_forward_bn: running statistics are NULL");
+    if (bn_mode != MVSN_BN_BATCH)
+        for (int i = 0; i < 16; ++i) MVSN_REQUIRE(running[i] != nullptr, MVSN_ENULL, "mvsn_featurenet_forward_bn: running[%d] is NULL", i);
     MVSN_REQUIRE(w && imgs && feats && workspace, MVSN_ENULL, "mvsn_featurenet_forward: NULL argument");
     MVSN_REQUIRE(V > 0 && H >= 4 && W >= 4, MVSN_EBADSHAPE, "mvsn_featurenet_forward: bad shape V=%d H=%d W=%d", V, H, W);
     MVSN_REQUIRE(workspace_bytes >= mvsn_featurenet_workspace_bytes(V, H, W), MVSN_EWORKSPACE,
@@ -264,7 +274,7 @@ int mvsn_featurenet_forward(const float* const* w, const float* imgs, int V, int
 
     int hs[3] = {H, half_up(H), half_up(half_up(H))}, ws[3] = {W, half_up(W), half_up(half_up(W))};
     int rc;
-    ActSrc src{imgs, nullptr, nullptr, nullptr, 1.0};
+    ActSrc src{imgs, nullptr, nullptr, nullptr, 1.0, nullptr, nullptr};
     int hin = H, win = W;
     for (int l = 0; l < 8; ++l) {
         const int lv = kFLevel[l];
@@ -278,6 +288,9 @@ int mvsn_featurenet_forward(const float* const* w, const float* imgs, int V, int
         if (rc) return rc;
         src.x = a.out; src.stats = a.stats_out; src.gamma = w[3 * l + 1]; src.beta = w[3 * l + 2];
         src.count = (double)V * a.Hout * a.Wout;
+        if (bn_mode == MVSN_BN_RUNNING) { src.rmean = running[2 * l]; src.rvar = running[2 * l + 1]; }
+        if (bn_mode == MVSN_BN_BATCH_UPDATE)
+            bn_update_running_kernel<<<1, 64, 0, st>>>(a.stats_out, src.count, a.Cout, momentum, running[2 * l], running[2 * l + 1]);
         hin = a.Hout; win = a.Wout;
     }
     const long long plane = (long long)hin * win;

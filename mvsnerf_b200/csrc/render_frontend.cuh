@@ -72,6 +72,17 @@ int launch_render_tcs(const SceneDev& sc, const RenderIO& io, bool fast, const v
 size_t mlp_tcs_packed_bytes();
 int pack_mlp_tcs(const float* const* w, void* packed, cudaStream_t stream);
 int launch_render_tc2(const SceneDev& sc, const RenderIO& io, bool fast, const void* wimg, cudaStream_t stream);
+// fine-tuning step (render_bwd.cu)
+size_t render_backward_workspace_bytes(int N, int S);
+int launch_render_backward(const SceneDev& sc, const RenderIO& io, const float* wts_fp32, const float* const* mlp_w,
+                           const float* g_rgb, const float* target, float inv_count, const float* g_depth,
+                           const float* g_weights, const float* g_alpha, const float* g_feat, float* const* grad_mlp,
+                           float* dvol, float* rgb_out, float* depth_out, float* loss, void* workspace,
+                           size_t workspace_bytes, cudaStream_t stream);
+int launch_adam_tensors(float* const* p, const float* const* g, float* const* m, float* const* v, const int* n, int count,
+                        float lr, float beta1, float beta2, float eps, int step, cudaStream_t stream);
+int launch_adam_volume(float* p, float* g_dhwc, float* m, float* v, long long nvox, int planar, float lr, float beta1,
+                       float beta2, float eps, int step, cudaStream_t stream);
 size_t mlp_tc2_packed_bytes();
 int pack_mlp_tc2(const float* const* w, void* packed, cudaStream_t stream);
 

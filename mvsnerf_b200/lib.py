@@ -27,8 +27,11 @@ EXPORTS = [
     "mvsn_selftest_umma", "mvsn_debug_set_trace",
     "mvsn_peer_buffer_create", "mvsn_peer_buffer_open", "mvsn_peer_buffer_close", "mvsn_peer_buffer_destroy",
     "mvsn_render_rays_to_peers",
+    "mvsn_featurenet_forward_bn", "mvsn_costreg_forward_bn",
+    "mvsn_render_backward_workspace_bytes", "mvsn_render_backward", "mvsn_adam_step", "mvsn_adam_step_volume",
 ]
 MAX_PEERS, PEER_HANDLE_BYTES = 16, 64
+BN_BATCH, BN_BATCH_UPDATE, BN_RUNNING = 0, 1, 2
 
 
 class RenderScene(C.Structure):
@@ -40,6 +43,12 @@ class RenderScene(C.Structure):
 
 class PeerSink(C.Structure):
     _fields_ = [("frame", C.c_void_p * 16), ("n_peers", C.c_int), ("first_pixel", C.c_longlong)]
+
+
+class RenderGrads(C.Structure):
+    _fields_ = [("rgb", C.c_void_p), ("target_rgb", C.c_void_p), ("loss_scale", C.c_float), ("depth", C.c_void_p),
+                ("weights", C.c_void_p), ("alpha", C.c_void_p), ("input_feat", C.c_void_p), ("rgb_out", C.c_void_p),
+                ("depth_out", C.c_void_p), ("loss_out", C.c_void_p)]
 
 
 class RayParams(C.Structure):
@@ -85,6 +94,15 @@ def load() -> C.CDLL:
     lib.mvsn_peer_buffer_open.argtypes = [C.c_char_p, C.POINTER(vp)]
     lib.mvsn_peer_buffer_close.argtypes = [vp]
     lib.mvsn_peer_buffer_destroy.argtypes = [vp]
+    lib.mvsn_render_backward_workspace_bytes.restype = C.c_size_t
+    lib.mvsn_render_backward_workspace_bytes.argtypes = [ip, ip]
+    lib.mvsn_render_backward.argtypes = [C.POINTER(RenderScene), C.POINTER(vp), vp, vp, vp, vp, ip, ip,
+                                         C.POINTER(RenderGrads), C.POINTER(vp), vp, vp, C.c_size_t, vp]
+    lib.mvsn_adam_step.argtypes = [C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(ip), ip,
+                                   fp, fp, fp, fp, ip, vp]
+    lib.mvsn_adam_step_volume.argtypes = [vp, vp, vp, vp, C.c_longlong, ip, fp, fp, fp, fp, ip, vp]
+    lib.mvsn_costreg_forward_bn.argtypes = [C.POINTER(vp), C.POINTER(vp), ip, fp, vp, ip, ip, ip, vp, vp, C.c_size_t, vp]
+    lib.mvsn_featurenet_forward_bn.argtypes = [C.POINTER(vp), C.POINTER(vp), ip, fp, vp, ip, ip, ip, vp, vp, C.c_size_t, vp]
     lib.mvsn_debug_set_trace.argtypes = [vp]
     lib.mvsn_debug_set_trace.restype = None
     lib.mvsn_selftest_umma.argtypes = [vp, vp, vp, ip, ip, vp, vp]
@@ -92,7 +110,8 @@ def load() -> C.CDLL:
                  "mvsn_volume_from_channels_last", "mvsn_render_samples", "mvsn_render_rays",
                  "mvsn_build_cost_volume", "mvsn_costreg_forward", "mvsn_featurenet_forward",
                  "mvsn_render_rays_to_peers", "mvsn_peer_buffer_create", "mvsn_peer_buffer_open",
-                 "mvsn_peer_buffer_close", "mvsn_peer_buffer_destroy"):
+                 "mvsn_peer_buffer_close", "mvsn_peer_buffer_destroy", "mvsn_render_backward", "mvsn_adam_step",
+                 "mvsn_adam_step_volume", "mvsn_featurenet_forward_bn", "mvsn_costreg_forward_bn"):
         getattr(lib, name).restype = ip
     _lib = lib
     return lib

@@ -1,0 +1,57 @@
+"""GPU: the `self.training` dispatch of the encoder's BatchNorm ("implement both"; InPlaceABN,
+models.py:661-685).  eval mode = running statistics (pinned against the live reference's MVSNet.eval() in
+tests/test_oracle_pins.py through the oracle's eval_mode); train mode = batch statistics PLUS the in-place update of
+running_mean / running_var / num_batches_tracked that F.batch_norm(training=True) performs in the reference."""
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import mvsnerf_oracle as orc
+from mvsnerf_b200 import backend, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+WPATH = os.path.join(GOLDEN, "mvsnerf_v0_weights.npz")
+
+
+def test_eval_mode_uses_running_statistics(weights):
+    sc = synthetic.make_scene(64, 96, pad=4, seed=12)
+    d = sc.to(DEV)
+    mvs = backend.MVSNet().to(DEV)
+    backend.load_weights_npz(None, mvs, WPATH)
+    before = {k: v.clone() for k, v in mvs.state_dict().items()}
+    with torch.no_grad():
+        vol_eval, feats, _ = mvs.eval()(d.imgs_norm, d.proj_mats, sc.near_far, pad=sc.pad)
+    for k, v in mvs.state_dict().items():                       # eval mode touches no buffer
+        assert torch.equal(v, before[k]), k
+    ref = orc.encode_volume(sc.imgs_norm, sc.proj_mats, sc.near_far, sc.pad, weights, eval_mode=True)
+    assert (vol_eval.cpu() - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    f_ref = orc.feature_net(sc.imgs_norm[0], weights, eval_mode=True)
+    assert (feats[0].cpu() - f_ref).abs().max().item() <= 1e-4 * f_ref.abs().max().item()
+    # and it is a different function from train mode with this checkpoint (volume Linf ~7)
+    with torch.no_grad():
+        vol_train, _, _ = mvs.train()(d.imgs_norm, d.proj_mats, sc.near_far, pad=sc.pad)
+    assert (vol_train - vol_eval).abs().max().item() > 0.1
+
+
+def test_train_mode_updates_running_statistics_like_batch_norm(weights):
+    sc = synthetic.make_scene(64, 96, pad=4, seed=13)
+    d = sc.to(DEV)
+    mvs = backend.MVSNet().to(DEV).train()
+    backend.load_weights_npz(None, mvs, WPATH)
+    rec = {}
+    ref = orc.encode_volume(sc.imgs_norm, sc.proj_mats, sc.near_far, sc.pad, weights, record=rec)
+    with torch.no_grad():
+        vol, _, _ = mvs(d.imgs_norm, d.proj_mats, sc.near_far, pad=sc.pad)
+    assert (vol.cpu() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    sd = mvs.state_dict()
+    assert len(rec) == 18
+    for name, (mean, var_unbiased) in rec.items():
+        key = name[len("mvs/"):]
+        want_m = 0.9 * weights[name + ".running_mean"] + 0.1 * mean
+        want_v = 0.9 * weights[name + ".running_var"] + 0.1 * var_unbiased
+        assert (sd[key + ".running_mean"].cpu() - want_m).abs().max().item() <= 1e-4 * max(1.0, want_m.abs().max().item()), name
+        assert (sd[key + ".running_var"].cpu() - want_v).abs().max().item() <= 1e-4 * max(1.0, want_v.abs().max().item()), name
+        assert int(sd[key + ".num_batches_tracked"]) == int(weights[name + ".num_batches_tracked"]) + 1

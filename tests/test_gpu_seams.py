@@ -71,7 +71,8 @@ def test_create_nerf_mvs_factory(ckpt_tar, scene):
     with torch.no_grad():
         vol, _, _ = mvs(d.imgs_norm, d.proj_mats, sc.near_far, pad=sc.pad)
         vol2, _, _ = mvs2.train()(d.imgs_norm, d.proj_mats, sc.near_far, pad=sc.pad)
-    assert torch.equal(vol, vol2)
+    # same weights, same inputs: equal up to the summation order of the BatchNorm statistics (fp64 atomics across CTAs)
+    assert (vol - vol2).abs().max().item() < 1e-5
     # alpha-only query function (renderer.py:42-63) still answers
     x = torch.rand(7, 5, 3, device=DEV)
     out = train["network_query_fn"](x, None, torch.rand(7, 5, 20, device=DEV), fn)
@@ -104,8 +105,8 @@ def test_return_color(scene, weights):
     hp, wp = sc.H // 4 + 2 * sc.pad, sc.W // 4 + 2 * sc.pad
     assert feats.shape == (1, 3, 4, 128, hp, wp) and depth_values.shape == (1, 128)
     f = orc.feature_net(sc.imgs_norm[0], weights)
-    cost, masks = orc.cost_volume(sc.imgs_norm, f[None], sc.proj_mats, orc.depth_planes(*sc.near_far)[None], sc.pad)
-    ref = torch.cat((cost[:, :9].view(1, 3, 3, *cost.shape[2:]), masks.unsqueeze(2)), dim=2)
+    cost, masks = orc.cost_volume(sc.imgs_norm[0], f, sc.proj_mats[0], orc.depth_planes(*sc.near_far), sc.pad)
+    ref = torch.cat((cost[:9].view(1, 3, 3, *cost.shape[1:]), masks[None].unsqueeze(2)), dim=2)
     assert torch.equal(feats[:, :, 3].cpu(), ref[:, :, 3])                      # masks exactly
     assert (feats[:, :, :3].cpu() - ref[:, :, :3]).abs().max() < 1e-4
 
@@ -147,7 +148,7 @@ def test_volume_cache_hits_for_planar_volumes(scene):
         assert backend.cache_stats["miss"] - m0 == 2 and backend.cache_stats["hit"] - h0 == 4
         direct = backend.render_rays(rays, vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(sc.pad), N_samples=32)
         assert torch.equal(outs[0][0], direct[0]) and torch.equal(outs[2][0], direct[0])
-        ref_vol.feat_volume.data.mul_(0.5)                                        # in-place update (an optimiser step)
+        ref_vol.feat_volume.mul_(0.5)                                             # in-place update, as an optimiser step does it (under no_grad)
         changed = backend.render_rays(rays, ref_vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(sc.pad), N_samples=32)
         assert not torch.equal(changed[0], direct[0])
 

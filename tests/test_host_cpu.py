@@ -78,7 +78,7 @@ def test_no_silent_cpu_fallback():
         backend.render_rays(synthetic.scene_rays(sc), torch.zeros(1, 8, 128, 16, 16), sc.imgs_raw, sc.pose_source,
                             fn, sc.near_far, 4.0)
     with pytest.raises(RuntimeError):
-        backend.MVSNet().eval()(sc.imgs_norm, sc.proj_mats, sc.near_far)
+        backend.MVSNet().eval()(sc.imgs_norm, sc.proj_mats, sc.near_far)       # eval mode exists, but not on the CPU
 
 
 def test_synthetic_scene_contract():
@@ -140,6 +140,7 @@ def test_autograd_plumbing_of_rendering(monkeypatch):
                                              pose_ref["w2cs"], pose_ref["intrinsics"], network_fn, white_bkgd)
 
     monkeypatch.setattr(backend, "_render_samples_kernel", fake_kernel)
+    monkeypatch.setattr(backend, "BACKWARD_IMPL", "torch")       # the kernel backward needs a GPU (tests/test_gpu_backward.py)
 
     class A:
         use_color_volume = False

@@ -43,3 +43,22 @@ def test_live_reference_vs_oracle(live, weights):
                                  sc.near_far, float(sc.pad), n_samples=24)
     assert (rgb - rgb_ref).abs().max() < 2e-6
     assert (depth - depth_ref).abs().max() < 1e-5
+
+
+def test_live_reference_eval_mode_vs_oracle(live, weights):
+    """MVSNet.eval() (running-statistics BatchNorm, models.py:661-685 through the InPlaceABN stub) vs the oracle's eval_mode."""
+    sc = synthetic.make_scene(64, 96, pad=4, seed=12)
+    live.mvsnet.eval()
+    try:
+        with torch.no_grad():
+            vol_ref, _, _ = live.mvsnet(sc.imgs_norm, sc.proj_mats, sc.near_far, pad=sc.pad)
+    finally:
+        live.mvsnet.train()
+    # the live module's running statistics, not the checkpoint's: every train-mode forward of the reference (the other
+    # tests of this module ran some) updates them in place -- the side effect MVSN_BN_BATCH_UPDATE reproduces
+    w = dict(weights)
+    w.update({"mvs/" + k: v.detach().clone() for k, v in live.mvsnet.state_dict().items()})
+    vol = orc.encode_volume(sc.imgs_norm, sc.proj_mats, sc.near_far, sc.pad, w, eval_mode=True)
+    assert (vol - vol_ref).abs().max() < 2e-4 * max(1.0, float(vol_ref.abs().max()))
+    vol_train = orc.encode_volume(sc.imgs_norm, sc.proj_mats, sc.near_far, sc.pad, weights)
+    assert (vol - vol_train).abs().max() > 0.1          # the two modes differ grossly with this checkpoint (SURVEY App. D)
