@@ -284,6 +284,8 @@ def run_ours(args):
     px_all = torch.empty(world * N_RAYS, 4, device=dev) if assemble == "nccl" else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)                  # > 126 MB L2
     launches = [0]
+    local_sink = lib.PeerSink()                                                    # NCCL path: one [n,4] send buffer
+    local_sink.frame[0], local_sink.n_peers, local_sink.first_pixel = px_local.data_ptr(), 1, 0
 
     def step(i, m=mode, kev=None):
         """One step: this rank's frame through the render kernel; at N > 1 the job's frames assembled on every rank."""
@@ -292,6 +294,8 @@ def run_ours(args):
             kev[0].record()
         if assemble == "peer":
             render(r, m, sink=frame.sink(rank * N_RAYS))
+        elif assemble == "nccl":
+            render(r, m, sink=local_sink)                # packed (r,g,b,depth) texels straight from the epilogue
         else:
             render(r, m, out=(rgb, depth))
         if kev:
@@ -301,7 +305,6 @@ def run_ours(args):
             frame.complete()
             frame.rotate()
         elif assemble == "nccl":
-            px_local[:, :3].copy_(rgb); px_local[:, 3].copy_(depth)
             dist.all_gather_into_tensor(px_all, px_local)
 
     def timed_steps(m, n_warm, n_steps):
@@ -362,11 +365,9 @@ def run_ours(args):
                                N_samples=S, mlp_mode=m, sink=frame.sink(rank * N_RAYS), after_launch=frame.complete)
                     frame.rotate()
                 elif assemble == "nccl":
-                    def gather():
-                        px_local[:, :3].copy_(hfr.rgb_dev); px_local[:, 3].copy_(hfr.depth_dev)
-                        dist.all_gather_into_tensor(px_all, px_local)
                     hfr.render(rays_host[i % n_distinct], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD),
-                               N_samples=S, mlp_mode=m, after_launch=gather)
+                               N_samples=S, mlp_mode=m, sink=local_sink,
+                               after_launch=lambda: dist.all_gather_into_tensor(px_all, px_local))
                 else:
                     hfr.render(rays_host[i % n_distinct], vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD),
                                N_samples=S, mlp_mode=m)
