@@ -355,6 +355,18 @@ def run_ours(args):
                              "assembly = what follows it inside the step (peer: 1-element barrier; nccl: pack + all-gather), "
                              "including the wait for the slowest rank"}
 
+        # ---- the NCCL alternative on the same steps, for the record (peer-store runs only) ----------------------
+        alt = None
+        if assemble == "peer" and not args.no_assembly_comparison:
+            assemble = "nccl"
+            px_all = torch.empty(world * N_RAYS, 4, device=dev)
+            ms_n, kern_n, rest_n = timed_steps(mode, 3, args.steps)
+            alt = {"assemble": "one NCCL all_gather_into_tensor of packed [n,4] pixels per step", "ms_per_step": ms_n,
+                   "value": world * N_RAYS / (ms_n * 1e-3), "unit": "rays/s",
+                   "render_ms_median": _median(kern_n), "assembly_ms_median": _median(rest_n), "assembly_ms_max": max(rest_n)}
+            assemble = "peer"
+            px_all = None
+
         # ---- e2e: host rays -> H2D -> kernel -> (assembly) -> D2H, through the host-buffer call ---------
         def e2e_run(m, n_steps):
             hfr = backend.HostFrameRenderer(N_RAYS, dev)
@@ -499,6 +511,8 @@ def run_ours(args):
         }
         if trace:
             line["step_trace"] = trace
+        if alt:
+            line["assembly_comparison"] = alt
         if why:
             line["config"]["peer_store_fallback"] = why
         line.update(other)
@@ -585,6 +599,7 @@ def main():
     ap.add_argument("--no-fp32-tier", action="store_true")
     ap.add_argument("--no-torch-gpu", action="store_true")
     ap.add_argument("--no-finetune", action="store_true")
+    ap.add_argument("--no-assembly-comparison", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

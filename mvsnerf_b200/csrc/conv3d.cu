@@ -28,7 +28,7 @@ struct ConvArgs {
 // write 4 x CT raw outputs + accumulate batch statistics
 template <int CT>
 __device__ __forceinline__ void store_and_stats(const ConvArgs& a, float (&acc)[4][CT], bool active, int z, int y,
-                                                int x0, int cg, float* s_stat, int tid) {
+                                                int x0, int cg, unsigned long long* s_stat, int tid) {
     const int lane = tid & 31;
     const size_t plane = (size_t)a.Hout * a.Wout, vol = plane * a.Dout;
     const bool vec = (a.Wout & 3) == 0;
@@ -52,10 +52,10 @@ __device__ __forceinline__ void store_and_stats(const ConvArgs& a, float (&acc)[
             s += __shfl_xor_sync(0xffffffffu, s, off);
             q += __shfl_xor_sync(0xffffffffu, q, off);
         }
-        if (lane == 0) { atomicAdd(&s_stat[2 * c], s); atomicAdd(&s_stat[2 * c + 1], q); }
+        if (lane == 0) { atomicAdd(&s_stat[2 * c], stat_fx(s)); atomicAdd(&s_stat[2 * c + 1], stat_fx(q)); }
     }
     __syncthreads();
-    if (tid < 2 * CT) atomicAdd(&a.stats_out[2 * (cg * CT) + tid], (double)s_stat[tid]);
+    if (tid < 2 * CT) atomicAdd(reinterpret_cast<unsigned long long*>(a.stats_out) + 2 * (cg * CT) + tid, s_stat[tid]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128)
 conv3d_k3_kernel(const ConvArgs a) {
     extern __shared__ __align__(16) float s_w[];            // [Cin][27][CT]
     __shared__ float s_sc[kMaxCin], s_sh[kMaxCin];
-    __shared__ float s_stat[2 * CT];
+    __shared__ unsigned long long s_stat[2 * CT];   // fixed-point partial sums (stat_fx): order-independent
     const int tid = threadIdx.x, lane = tid & 31;
     const int cg = blockIdx.y;
 
@@ -76,7 +76,7 @@ conv3d_k3_kernel(const ConvArgs a) {
         s_w[i] = __ldg(a.w + (size_t)(cg * CT + c) * a.Cin * 27 + r);
     }
     if (!IDENT) load_norm(a.in0, a.Cin, s_sc, s_sh, tid, 128);
-    if (tid < 2 * CT) s_stat[tid] = 0.f;
+    if (tid < 2 * CT) s_stat[tid] = 0ull;
     __syncthreads();
 
     const int nsx = (a.Wout + 3) >> 2;
@@ -205,14 +205,14 @@ __global__ void __launch_bounds__(128, 4)
 conv0_k3_kernel(const ConvArgs a) {
     constexpr int CT = 8;
     extern __shared__ __align__(16) float s_w[];            // [Cin][27][8]
-    __shared__ float s_stat[2 * CT];
+    __shared__ unsigned long long s_stat[2 * CT];   // fixed-point partial sums (stat_fx): order-independent
     const int tid = threadIdx.x, lane = tid & 31;
 
     for (int i = tid; i < a.Cin * 27 * CT; i += 128) {
         const int c = i % CT, r = i / CT;
         s_w[i] = __ldg(a.w + (size_t)c * a.Cin * 27 + r);
     }
-    if (tid < 2 * CT) s_stat[tid] = 0.f;
+    if (tid < 2 * CT) s_stat[tid] = 0ull;
     __syncthreads();
 
     const int W = a.Win, H = a.Hin, D = a.Din;
@@ -316,10 +316,10 @@ conv0_k3_kernel(const ConvArgs a) {
             s += __shfl_xor_sync(0xffffffffu, s, off);
             q += __shfl_xor_sync(0xffffffffu, q, off);
         }
-        if (lane == 0) { atomicAdd(&s_stat[2 * c], s); atomicAdd(&s_stat[2 * c + 1], q); }
+        if (lane == 0) { atomicAdd(&s_stat[2 * c], stat_fx(s)); atomicAdd(&s_stat[2 * c + 1], stat_fx(q)); }
     }
     __syncthreads();
-    if (tid < 2 * CT) atomicAdd(&a.stats_out[tid], (double)s_stat[tid]);
+    if (tid < 2 * CT) atomicAdd(reinterpret_cast<unsigned long long*>(a.stats_out) + tid, s_stat[tid]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -337,7 +337,7 @@ deconv3d_subpixel_kernel(const ConvArgs a) {
     constexpr int CT = 8;
     extern __shared__ __align__(16) float s_w[];            // [Cin][27][CT]
     __shared__ float s_sc[2][kMaxCin], s_sh[2][kMaxCin];
-    __shared__ float s_stat[2 * CT];
+    __shared__ unsigned long long s_stat[2 * CT];   // fixed-point partial sums (stat_fx): order-independent
     const int tid = threadIdx.x, lane = tid & 31;
     const int cg = blockIdx.y;
     const bool dual = a.in1.x != nullptr;
@@ -348,7 +348,7 @@ deconv3d_subpixel_kernel(const ConvArgs a) {
     }
     load_norm(a.in0, a.Cin, s_sc[0], s_sh[0], tid, 128);
     if (dual) load_norm(a.in1, a.Cin, s_sc[1], s_sh[1], tid, 128);
-    if (tid < 2 * CT) s_stat[tid] = 0.f;
+    if (tid < 2 * CT) s_stat[tid] = 0ull;
     __syncthreads();
 
     const long long nin = (long long)a.Din * a.Hin * a.Win;
@@ -448,10 +448,10 @@ deconv3d_subpixel_kernel(const ConvArgs a) {
             s += __shfl_xor_sync(0xffffffffu, s, off);
             q += __shfl_xor_sync(0xffffffffu, q, off);
         }
-        if (lane == 0) { atomicAdd(&s_stat[2 * c], s); atomicAdd(&s_stat[2 * c + 1], q); }
+        if (lane == 0) { atomicAdd(&s_stat[2 * c], stat_fx(s)); atomicAdd(&s_stat[2 * c + 1], stat_fx(q)); }
     }
     __syncthreads();
-    if (tid < 2 * CT) atomicAdd(&a.stats_out[2 * (cg * CT) + tid], (double)s_stat[tid]);
+    if (tid < 2 * CT) atomicAdd(reinterpret_cast<unsigned long long*>(a.stats_out) + 2 * (cg * CT) + tid, s_stat[tid]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -526,8 +526,8 @@ __global__ void bn_update_running_kernel(const double* __restrict__ stats, doubl
                                          float* __restrict__ rmean, float* __restrict__ rvar) {
     const int c = threadIdx.x;
     if (c >= C) return;
-    const double mean = stats[2 * c] / count;
-    double var = stats[2 * c + 1] / count - mean * mean;
+    const double mean = stat_value(stats + 2 * c) / count;
+    double var = stat_value(stats + 2 * c + 1) / count - mean * mean;
     var = var > 0.0 ? var : 0.0;
     const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
     rmean[c] = (float)((1.0 - (double)momentum) * (double)rmean[c] + (double)momentum * mean);

@@ -9,9 +9,23 @@ constexpr float kBnEps = 1e-5f;
 constexpr float kSlope = 0.01f;
 constexpr int kMaxCin = 64;
 
+// Batch statistics are accumulated as 64-bit FIXED-POINT integers (2^-16 resolution) in the `stats` slots, in shared
+// memory per CTA and with one global atomic per CTA and channel: integer addition is associative, so the statistics --
+// and therefore the whole encoding volume -- are bit-identical from run to run and from rank to rank (round 1 used
+// fp32 / fp64 floating-point atomics whose summation order made replicated builds differ in the last bits).
+// Range: |sum x^2| < 2^47 = 1.4e14 per channel; resolution 1.5e-5 per warp partial, far below the fp32 rounding of the
+// partial itself.
+constexpr double kStatScale = 65536.0;
+__device__ __forceinline__ unsigned long long stat_fx(float partial) {
+    return (unsigned long long)__double2ll_rn((double)partial * kStatScale);
+}
+__device__ __forceinline__ double stat_value(const double* slot) {
+    return (double)(*reinterpret_cast<const long long*>(slot)) * (1.0 / kStatScale);
+}
+
 struct ActSrc {                 // one input tensor of a layer, stored raw + its batch statistics
     const float* x;             // [C][D][H][W]
-    const double* stats;        // [C][2] sum, sum of squares over `count` voxels; null = plain tensor
+    const double* stats;        // [C][2] 64-bit slots: fixed-point sum, sum of squares over `count` voxels (stat_value); null = plain tensor
     const float* gamma;         // [C]
     const float* beta;          // [C]
     double count;
@@ -33,8 +47,8 @@ __device__ inline void load_norm(const ActSrc& s, int C, float* sc, float* sh, i
             if (s.rmean) {                                               // F.batch_norm(training=False)
                 mean = (double)s.rmean[c]; var = (double)s.rvar[c];
             } else {
-                mean = s.stats[2 * c] / s.count;
-                var = s.stats[2 * c + 1] / s.count - mean * mean;        // biased, as F.batch_norm(training=True)
+                mean = stat_value(s.stats + 2 * c) / s.count;
+                var = stat_value(s.stats + 2 * c + 1) / s.count - mean * mean;        // biased, as F.batch_norm(training=True)
             }
             var = var > 0.0 ? var : 0.0;
             const double inv = 1.0 / sqrt(var + (double)kBnEps);

@@ -30,7 +30,7 @@ conv2d_kernel(const Conv2dArgs a) {
     static_assert((3 * STRIDE + K - 1) - PAD - (NV - 1) == 1, "exactly one right-halo value");
     extern __shared__ __align__(16) float s_w[];            // [Cin][K*K][CT]
     __shared__ float s_sc[kMaxCin], s_sh[kMaxCin];
-    __shared__ float s_stat[2 * CT];
+    __shared__ unsigned long long s_stat[2 * CT];   // fixed-point partial sums (stat_fx): order-independent
     const int tid = threadIdx.x, lane = tid & 31;
     const int cg = blockIdx.y;
 
@@ -39,7 +39,7 @@ conv2d_kernel(const Conv2dArgs a) {
         s_w[i] = __ldg(a.w + (size_t)(cg * CT + c) * a.Cin * K * K + r);
     }
     if (!IDENT) load_norm(a.in, a.Cin, s_sc, s_sh, tid, 128);
-    if (tid < 2 * CT) s_stat[tid] = 0.f;
+    if (tid < 2 * CT) s_stat[tid] = 0ull;
     __syncthreads();
 
     const int nsx = (a.Wout + 3) >> 2;
@@ -164,10 +164,10 @@ conv2d_kernel(const Conv2dArgs a) {
             s += __shfl_xor_sync(0xffffffffu, s, off);
             q += __shfl_xor_sync(0xffffffffu, q, off);
         }
-        if (lane == 0) { atomicAdd(&s_stat[2 * c], s); atomicAdd(&s_stat[2 * c + 1], q); }
+        if (lane == 0) { atomicAdd(&s_stat[2 * c], stat_fx(s)); atomicAdd(&s_stat[2 * c + 1], stat_fx(q)); }
     }
     __syncthreads();
-    if (tid < 2 * CT) atomicAdd(&a.stats_out[2 * (cg * CT) + tid], (double)s_stat[tid]);
+    if (tid < 2 * CT) atomicAdd(reinterpret_cast<unsigned long long*>(a.stats_out) + 2 * (cg * CT) + tid, s_stat[tid]);
 }
 
 // toplayer: feats = W (32x32) . ABN(conv2.2) + b, one thread per pixel, weights broadcast from shared memory

@@ -36,6 +36,13 @@ def main():
     report, bad = {"world": world}, 0
     with torch.no_grad():
         vol, _, _ = mvs(d.imgs_norm, d.proj_mats, sc.near_far, pad=sc.pad)
+        # replicated builds must be bit-identical (fixed-point BatchNorm statistics): compare with rank 0's copy
+        vol0 = vol.contiguous().clone()
+        dist.broadcast(vol0, 0)
+        same = torch.tensor([float(torch.equal(vol, vol0))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        report["replicated_volume_bit_identical"] = bool(same.item() > 0)
+        bad += int(same.item() < 1)
         rays_all = synthetic.scene_rays(sc).to(dev)
         for name, rays in (("frame_4096", rays_all), ("ragged_1001", rays_all[:1001].contiguous())):
             n = rays.shape[0]
