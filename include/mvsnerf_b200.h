@@ -258,6 +258,8 @@ int mvsn_costreg_forward(const float* const* w_host_array_of_device_ptrs, const 
 #define MVSN_BN_BATCH         0
 #define MVSN_BN_BATCH_UPDATE  1
 #define MVSN_BN_RUNNING       2
+#define MVSN_CONV0_FFMA       0x100 /* diagnostic flag, OR-ed into bn_mode of mvsn_costreg_forward_bn: run the first layer
+                                       (41 -> 8 channels) on the fp32 FFMA kernel instead of the tcgen05 kernel */
 int mvsn_featurenet_forward_bn(const float* const* w_host_array_of_device_ptrs, float* const* running, int bn_mode,
                                float momentum, const float* imgs, int V, int H, int W, float* feats,
                                void* workspace, size_t workspace_bytes, void* stream);

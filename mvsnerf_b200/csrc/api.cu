@@ -103,6 +103,7 @@ __global__ void pack_mlp_fp32_kernel(MlpPtrs w, float* __restrict__ out) {
 }
 
 static long long* g_trace = nullptr;
+long long* debug_trace_buffer() { return g_trace; }     // trace builds only (conv0_tc.cu role profile)
 
 static int make_scene(const mvsn_render_scene* s, SceneDev& d) {
     MVSN_REQUIRE(s != nullptr, MVSN_ENULL, "scene is NULL");

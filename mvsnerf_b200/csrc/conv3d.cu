@@ -16,14 +16,6 @@
 
 namespace mvsn {
 
-struct ConvArgs {
-    ActSrc in0, in1;            // in1.x == null unless the layer input is a skip sum
-    int Cin, Din, Hin, Win;
-    const float* w;             // Conv3d [Cout][Cin][27] or ConvTranspose3d [Cin][Cout][27]
-    int Cout, Dout, Hout, Wout;
-    float* out;                 // [Cout][Dout][Hout][Wout] raw
-    double* stats_out;          // [Cout][2]
-};
 
 // write 4 x CT raw outputs + accumulate batch statistics
 template <int CT>
@@ -550,6 +542,7 @@ extern "C" {
 size_t mvsn_costreg_workspace_bytes(int D, int Hp, int Wp) {
     size_t total = 4096;                                       // statistics block (10 layers x <=64 ch x 2 doubles)
     total += 10 * 64 * 2 * sizeof(double);
+    total += align_up(conv0_tc_workspace_bytes(), 4096);        // conv0's tensor-core weight image (hi | lo)
     for (int l = 0; l < 10; ++l) {
         const int s = 1 << kLevelOut[l];
         total += align_up((size_t)kCout[l] * (D / s) * (Hp / s) * (Wp / s) * sizeof(float), 256);
@@ -565,6 +558,8 @@ int mvsn_costreg_forward(const float* const* w, const float* cost, int D, int Hp
 int mvsn_costreg_forward_bn(const float* const* w, float* const* running, int bn_mode, float momentum, const float* cost,
                             int D, int Hp, int Wp, float* volume_dhwc, void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
+    const bool conv0_ffma_flag = (bn_mode & MVSN_CONV0_FFMA) != 0;
+    bn_mode &= ~MVSN_CONV0_FFMA;
     MVSN_REQUIRE(bn_mode == MVSN_BN_BATCH || bn_mode == MVSN_BN_BATCH_UPDATE || bn_mode == MVSN_BN_RUNNING, MVSN_EBADSHAPE,
                  "mvsn_costreg_forward_bn: bn_mode %d", bn_mode);
     MVSN_REQUIRE(bn_mode == MVSN_BN_BATCH || running, MVSN_ENULL, "mvsn_costreg_forward_bn: running statistics are NULL");
@@ -586,6 +581,8 @@ int mvsn_costreg_forward_bn(const float* const* w, float* const* running, int bn
     double* stats = reinterpret_cast<double*>(p);
     const size_t stats_bytes = 10 * 64 * 2 * sizeof(double);
     p += align_up(stats_bytes, 4096);
+    void* conv0_wimg = p;
+    p += align_up(conv0_tc_workspace_bytes(), 4096);
     float* raw[10];
     Dims dims[10];
     for (int l = 0; l < 10; ++l) {
@@ -615,7 +612,12 @@ int mvsn_costreg_forward_bn(const float* const* w, float* const* running, int bn
     int rc;
     ActSrc cost_src{cost, nullptr, nullptr, nullptr, 1.0, nullptr, nullptr};
     const Dims full{D, Hp, Wp};
-    if ((rc = launch_conv0(args(0, cost_src, none, full), st))) return rc;                     // conv0 41->8
+    // conv0 41->8: tcgen05 kernel (conv0_tc.cu); the MVSN_CONV0_FFMA flag (or MVSN_CONV0=ffma in the environment) selects
+    // the round-1 FFMA kernel for A/B comparisons
+    static const bool conv0_ffma_env = [] { const char* e = getenv("MVSN_CONV0"); return e && !strcmp(e, "ffma"); }();
+    if (conv0_ffma_env || conv0_ffma_flag) rc = launch_conv0(args(0, cost_src, none, full), st);
+    else rc = launch_conv0_tc(args(0, cost_src, none, full), conv0_wimg, st);
+    if (rc) return rc;
     if ((rc = launch_conv_auto<2>(args(1, src(0), none, dims[0]), st))) return rc;       // conv1 8->16 s2
     if ((rc = launch_conv_auto<1>(args(2, src(1), none, dims[1]), st))) return rc;       // conv2 16->16
     if ((rc = launch_conv_auto<2>(args(3, src(2), none, dims[2]), st))) return rc;       // conv3 16->32 s2

@@ -2,6 +2,7 @@
 // train-mode InPlaceABN folded into the consumer's load ("normalise on load").
 #pragma once
 #include "common.cuh"
+#include <cstdlib>
 
 namespace mvsn {
 
@@ -60,6 +61,17 @@ __device__ inline void load_norm(const ActSrc& s, int C, float* sc, float* sh, i
         }
     }
 }
+
+struct ConvArgs {               // one 3-D (transposed) convolution layer of CostRegNet (conv3d.cu, conv0_tc.cu)
+    ActSrc in0, in1;            // in1.x == null unless the layer input is a skip sum
+    int Cin, Din, Hin, Win;
+    const float* w;             // Conv3d [Cout][Cin][27] or ConvTranspose3d [Cin][Cout][27]
+    int Cout, Dout, Hout, Wout;
+    float* out;                 // [Cout][Dout][Hout][Wout] raw
+    double* stats_out;          // [Cout][2] fixed-point slots
+};
+size_t conv0_tc_workspace_bytes();
+int launch_conv0_tc(const ConvArgs& a, void* wimg, cudaStream_t st);
 
 // train mode side effect of F.batch_norm: running = (1 - momentum) running + momentum batch (variance UNBIASED, n / (n - 1))
 __global__ void bn_update_running_kernel(const double* __restrict__ stats, double count, int C, float momentum,

@@ -32,6 +32,7 @@ EXPORTS = [
 ]
 MAX_PEERS, PEER_HANDLE_BYTES = 16, 64
 BN_BATCH, BN_BATCH_UPDATE, BN_RUNNING = 0, 1, 2
+CONV0_FFMA = 0x100
 
 
 class RenderScene(C.Structure):

@@ -55,3 +55,31 @@ def test_train_mode_updates_running_statistics_like_batch_norm(weights):
         assert (sd[key + ".running_mean"].cpu() - want_m).abs().max().item() <= 1e-4 * max(1.0, want_m.abs().max().item()), name
         assert (sd[key + ".running_var"].cpu() - want_v).abs().max().item() <= 1e-4 * max(1.0, want_v.abs().max().item()), name
         assert int(sd[key + ".num_batches_tracked"]) == int(weights[name + ".num_batches_tracked"]) + 1
+
+
+@pytest.mark.parametrize("D,Hp,Wp", [(16, 24, 40), (24, 16, 64), (16, 40, 72), (32, 48, 56)])
+def test_conv0_tensor_core_kernel_vs_ffma_kernel(D, Hp, Wp):
+    """conv0 on tcgen05 (csrc/conv0_tc.cu: TMA-staged tiles, 2-term fp16 split, shifted-tap epilogue) against the
+    round-1 FFMA kernel through the whole CostRegNet, on volumes whose sizes are not multiples of the 6 x 10 x 30 brick
+    (partial bricks in every direction), and bit-identical from run to run.  (Volumes whose coarsest level has only a
+    voxel or two are left out: BatchNorm over one voxel divides by sqrt(eps) and turns 1e-6 into 1e-3.)"""
+    import ctypes as C
+    from mvsnerf_b200 import lib
+    L = lib.load()
+    mvs = backend.MVSNet().to(DEV).train()
+    backend.load_weights_npz(None, mvs, WPATH)
+    reg = mvs.cost_reg_2
+    g = torch.Generator(device=DEV).manual_seed(D * 1000 + Wp)
+    cost = torch.randn(1, 41, D, Hp, Wp, device=DEV, generator=g) * torch.linspace(0.05, 30.0, 41, device=DEV).view(1, 41, 1, 1, 1)
+    weights = [w.detach().contiguous() for w in reg.weight_list()]
+    ws_bytes = L.mvsn_costreg_workspace_bytes(D, Hp, Wp)
+    outs = []
+    for flags in (lib.BN_BATCH, lib.BN_BATCH, lib.BN_BATCH | lib.CONV0_FFMA):
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=DEV)
+        vol = torch.empty(D, Hp, Wp, 8, device=DEV)
+        lib.check(L.mvsn_costreg_forward_bn(lib.ptr_array(weights), None, flags, 0.0, lib.ptr(cost), D, Hp, Wp, lib.ptr(vol),
+                                            lib.ptr(ws), ws_bytes, lib.stream_ptr()), "mvsn_costreg_forward_bn")
+        outs.append(vol)
+    assert torch.equal(outs[0], outs[1])                                   # deterministic
+    scale = outs[2].abs().max().item()
+    assert (outs[0] - outs[2]).abs().max().item() <= 2e-5 * scale, ((outs[0] - outs[2]).abs().max().item(), scale)
