@@ -20,7 +20,7 @@ namespace mvsn {
 // write 4 x CT raw outputs + accumulate batch statistics
 template <int CT>
 __device__ __forceinline__ void store_and_stats(const ConvArgs& a, float (&acc)[4][CT], bool active, int z, int y,
-                                                int x0, int cg, unsigned long long* s_stat, int tid) {
+                                                int x0, int cg, float* s_stat, int tid) {
     const int lane = tid & 31;
     const size_t plane = (size_t)a.Hout * a.Wout, vol = plane * a.Dout;
     const bool vec = (a.Wout & 3) == 0;
@@ -44,10 +44,12 @@ __device__ __forceinline__ void store_and_stats(const ConvArgs& a, float (&acc)[
             s += __shfl_xor_sync(0xffffffffu, s, off);
             q += __shfl_xor_sync(0xffffffffu, q, off);
         }
-        if (lane == 0) { atomicAdd(&s_stat[2 * c], stat_fx(s)); atomicAdd(&s_stat[2 * c + 1], stat_fx(q)); }
+        if (lane == 0) { s_stat[(tid >> 5) * 2 * CT + 2 * c] = s; s_stat[(tid >> 5) * 2 * CT + 2 * c + 1] = q; }
     }
     __syncthreads();
-    if (tid < 2 * CT) atomicAdd(reinterpret_cast<unsigned long long*>(a.stats_out) + 2 * (cg * CT) + tid, s_stat[tid]);
+    if (tid < 2 * CT)       // four warp partials -> fixed point -> ONE integer atomic per CTA and slot (order-independent)
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.stats_out) + 2 * (cg * CT) + tid,
+                  stat_fx(s_stat[tid]) + stat_fx(s_stat[2 * CT + tid]) + stat_fx(s_stat[4 * CT + tid]) + stat_fx(s_stat[6 * CT + tid]));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -59,7 +61,7 @@ __global__ void __launch_bounds__(128)
 conv3d_k3_kernel(const ConvArgs a) {
     extern __shared__ __align__(16) float s_w[];            // [Cin][27][CT]
     __shared__ float s_sc[kMaxCin], s_sh[kMaxCin];
-    __shared__ unsigned long long s_stat[2 * CT];   // fixed-point partial sums (stat_fx): order-independent
+    __shared__ float s_stat[4 * 2 * CT];            // per-warp partial sums (4 warps), combined in fixed point
     const int tid = threadIdx.x, lane = tid & 31;
     const int cg = blockIdx.y;
 
@@ -68,7 +70,7 @@ conv3d_k3_kernel(const ConvArgs a) {
         s_w[i] = __ldg(a.w + (size_t)(cg * CT + c) * a.Cin * 27 + r);
     }
     if (!IDENT) load_norm(a.in0, a.Cin, s_sc, s_sh, tid, 128);
-    if (tid < 2 * CT) s_stat[tid] = 0ull;
+    
     __syncthreads();
 
     const int nsx = (a.Wout + 3) >> 2;
@@ -197,14 +199,14 @@ __global__ void __launch_bounds__(128, 4)
 conv0_k3_kernel(const ConvArgs a) {
     constexpr int CT = 8;
     extern __shared__ __align__(16) float s_w[];            // [Cin][27][8]
-    __shared__ unsigned long long s_stat[2 * CT];   // fixed-point partial sums (stat_fx): order-independent
+    __shared__ float s_stat[4 * 2 * CT];            // per-warp partial sums (4 warps), combined in fixed point
     const int tid = threadIdx.x, lane = tid & 31;
 
     for (int i = tid; i < a.Cin * 27 * CT; i += 128) {
         const int c = i % CT, r = i / CT;
         s_w[i] = __ldg(a.w + (size_t)c * a.Cin * 27 + r);
     }
-    if (tid < 2 * CT) s_stat[tid] = 0ull;
+    
     __syncthreads();
 
     const int W = a.Win, H = a.Hin, D = a.Din;
@@ -308,10 +310,12 @@ conv0_k3_kernel(const ConvArgs a) {
             s += __shfl_xor_sync(0xffffffffu, s, off);
             q += __shfl_xor_sync(0xffffffffu, q, off);
         }
-        if (lane == 0) { atomicAdd(&s_stat[2 * c], stat_fx(s)); atomicAdd(&s_stat[2 * c + 1], stat_fx(q)); }
+        if (lane == 0) { s_stat[(tid >> 5) * 2 * CT + 2 * c] = s; s_stat[(tid >> 5) * 2 * CT + 2 * c + 1] = q; }
     }
     __syncthreads();
-    if (tid < 2 * CT) atomicAdd(reinterpret_cast<unsigned long long*>(a.stats_out) + tid, s_stat[tid]);
+    if (tid < 2 * CT)
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.stats_out) + tid,
+                  stat_fx(s_stat[tid]) + stat_fx(s_stat[2 * CT + tid]) + stat_fx(s_stat[4 * CT + tid]) + stat_fx(s_stat[6 * CT + tid]));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -329,7 +333,7 @@ deconv3d_subpixel_kernel(const ConvArgs a) {
     constexpr int CT = 8;
     extern __shared__ __align__(16) float s_w[];            // [Cin][27][CT]
     __shared__ float s_sc[2][kMaxCin], s_sh[2][kMaxCin];
-    __shared__ unsigned long long s_stat[2 * CT];   // fixed-point partial sums (stat_fx): order-independent
+    __shared__ float s_stat[4 * 2 * CT];            // per-warp partial sums (4 warps), combined in fixed point
     const int tid = threadIdx.x, lane = tid & 31;
     const int cg = blockIdx.y;
     const bool dual = a.in1.x != nullptr;
@@ -340,7 +344,7 @@ deconv3d_subpixel_kernel(const ConvArgs a) {
     }
     load_norm(a.in0, a.Cin, s_sc[0], s_sh[0], tid, 128);
     if (dual) load_norm(a.in1, a.Cin, s_sc[1], s_sh[1], tid, 128);
-    if (tid < 2 * CT) s_stat[tid] = 0ull;
+    
     __syncthreads();
 
     const long long nin = (long long)a.Din * a.Hin * a.Win;
@@ -440,10 +444,12 @@ deconv3d_subpixel_kernel(const ConvArgs a) {
             s += __shfl_xor_sync(0xffffffffu, s, off);
             q += __shfl_xor_sync(0xffffffffu, q, off);
         }
-        if (lane == 0) { atomicAdd(&s_stat[2 * c], stat_fx(s)); atomicAdd(&s_stat[2 * c + 1], stat_fx(q)); }
+        if (lane == 0) { s_stat[(tid >> 5) * 2 * CT + 2 * c] = s; s_stat[(tid >> 5) * 2 * CT + 2 * c + 1] = q; }
     }
     __syncthreads();
-    if (tid < 2 * CT) atomicAdd(reinterpret_cast<unsigned long long*>(a.stats_out) + 2 * (cg * CT) + tid, s_stat[tid]);
+    if (tid < 2 * CT)       // four warp partials -> fixed point -> ONE integer atomic per CTA and slot (order-independent)
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.stats_out) + 2 * (cg * CT) + tid,
+                  stat_fx(s_stat[tid]) + stat_fx(s_stat[2 * CT + tid]) + stat_fx(s_stat[4 * CT + tid]) + stat_fx(s_stat[6 * CT + tid]));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -514,16 +520,17 @@ static int launch_deconv(const ConvArgs& a, cudaStream_t st) {
     return MVSN_OK;
 }
 
-__global__ void bn_update_running_kernel(const double* __restrict__ stats, double count, int C, float momentum,
-                                         float* __restrict__ rmean, float* __restrict__ rvar) {
-    const int c = threadIdx.x;
-    if (c >= C) return;
-    const double mean = stat_value(stats + 2 * c) / count;
-    double var = stat_value(stats + 2 * c + 1) / count - mean * mean;
+__global__ void bn_update_running_kernel(BnUpdateArgs a) {
+    const int l = blockIdx.x, c = threadIdx.x;
+    if (c >= a.C[l]) return;
+    const double count = a.count[l];
+    const double mean = stat_value(a.stats[l] + 2 * c) / count;
+    double var = stat_value(a.stats[l] + 2 * c + 1) / count - mean * mean;
     var = var > 0.0 ? var : 0.0;
     const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    rmean[c] = (float)((1.0 - (double)momentum) * (double)rmean[c] + (double)momentum * mean);
-    rvar[c] = (float)((1.0 - (double)momentum) * (double)rvar[c] + (double)momentum * unbiased);
+    const double m = (double)a.momentum;
+    a.rmean[l][c] = (float)((1.0 - m) * (double)a.rmean[l][c] + m * mean);
+    a.rvar[l][c] = (float)((1.0 - m) * (double)a.rvar[l][c] + m * unbiased);
 }
 
 }  // namespace mvsn
@@ -631,10 +638,15 @@ int mvsn_costreg_forward_bn(const float* const* w, float* const* running, int bn
     finalize_volume_kernel<<<cdiv(nvox, 256) < sm_count() * 8 ? cdiv(nvox, 256) : sm_count() * 8, 256, 0, st>>>(
         src(0), src(9), nvox, reinterpret_cast<float4*>(volume_dhwc));
     MVSN_CUDA_CHECK(cudaGetLastError());
-    if (bn_mode == MVSN_BN_BATCH_UPDATE)
-        for (int l = 0; l < 10; ++l)
-            bn_update_running_kernel<<<1, 64, 0, st>>>(stats + (size_t)l * 128, (double)dims[l].n(), kCout[l], momentum,
-                                                       running[2 * l], running[2 * l + 1]);
+    if (bn_mode == MVSN_BN_BATCH_UPDATE) {
+        BnUpdateArgs u{};
+        for (int l = 0; l < 10; ++l) {
+            u.stats[l] = stats + (size_t)l * 128; u.count[l] = (double)dims[l].n(); u.C[l] = kCout[l];
+            u.rmean[l] = running[2 * l]; u.rvar[l] = running[2 * l + 1];
+        }
+        u.momentum = momentum;
+        bn_update_running_kernel<<<10, 64, 0, st>>>(u);
+    }
     MVSN_CUDA_CHECK(cudaGetLastError());
     return MVSN_OK;
 }

@@ -10,8 +10,8 @@ constexpr float kBnEps = 1e-5f;
 constexpr float kSlope = 0.01f;
 constexpr int kMaxCin = 64;
 
-// Batch statistics are accumulated as 64-bit FIXED-POINT integers (2^-16 resolution) in the `stats` slots, in shared
-// memory per CTA and with one global atomic per CTA and channel: integer addition is associative, so the statistics --
+// Batch statistics are accumulated as 64-bit FIXED-POINT integers (2^-16 resolution) in the `stats` slots: per CTA the
+// warps' fp32 partials are converted and summed as integers, then one global integer atomic per CTA and channel: integer addition is associative, so the statistics --
 // and therefore the whole encoding volume -- are bit-identical from run to run and from rank to rank (round 1 used
 // fp32 / fp64 floating-point atomics whose summation order made replicated builds differ in the last bits).
 // Range: |sum x^2| < 2^47 = 1.4e14 per channel; resolution 1.5e-5 per warp partial, far below the fp32 rounding of the
@@ -73,8 +73,16 @@ struct ConvArgs {               // one 3-D (transposed) convolution layer of Cos
 size_t conv0_tc_workspace_bytes();
 int launch_conv0_tc(const ConvArgs& a, void* wimg, cudaStream_t st);
 
-// train mode side effect of F.batch_norm: running = (1 - momentum) running + momentum batch (variance UNBIASED, n / (n - 1))
-__global__ void bn_update_running_kernel(const double* __restrict__ stats, double count, int C, float momentum,
-                                         float* __restrict__ rmean, float* __restrict__ rvar);
+// train mode side effect of F.batch_norm: running = (1 - momentum) running + momentum batch (variance UNBIASED, n / (n - 1));
+// one launch for all BatchNorm layers of a network (blockIdx.x = layer)
+struct BnUpdateArgs {
+    const double* stats[10];
+    double count[10];
+    int C[10];
+    float* rmean[10];
+    float* rvar[10];
+    float momentum;
+};
+__global__ void bn_update_running_kernel(BnUpdateArgs a);
 
 }  // namespace mvsn

@@ -30,7 +30,7 @@ conv2d_kernel(const Conv2dArgs a) {
     static_assert((3 * STRIDE + K - 1) - PAD - (NV - 1) == 1, "exactly one right-halo value");
     extern __shared__ __align__(16) float s_w[];            // [Cin][K*K][CT]
     __shared__ float s_sc[kMaxCin], s_sh[kMaxCin];
-    __shared__ unsigned long long s_stat[2 * CT];   // fixed-point partial sums (stat_fx): order-independent
+    __shared__ float s_stat[4 * 2 * CT];            // per-warp partial sums (4 warps), combined in fixed point
     const int tid = threadIdx.x, lane = tid & 31;
     const int cg = blockIdx.y;
 
@@ -39,7 +39,7 @@ conv2d_kernel(const Conv2dArgs a) {
         s_w[i] = __ldg(a.w + (size_t)(cg * CT + c) * a.Cin * K * K + r);
     }
     if (!IDENT) load_norm(a.in, a.Cin, s_sc, s_sh, tid, 128);
-    if (tid < 2 * CT) s_stat[tid] = 0ull;
+    
     __syncthreads();
 
     const int nsx = (a.Wout + 3) >> 2;
@@ -164,10 +164,12 @@ conv2d_kernel(const Conv2dArgs a) {
             s += __shfl_xor_sync(0xffffffffu, s, off);
             q += __shfl_xor_sync(0xffffffffu, q, off);
         }
-        if (lane == 0) { atomicAdd(&s_stat[2 * c], stat_fx(s)); atomicAdd(&s_stat[2 * c + 1], stat_fx(q)); }
+        if (lane == 0) { s_stat[(tid >> 5) * 2 * CT + 2 * c] = s; s_stat[(tid >> 5) * 2 * CT + 2 * c + 1] = q; }
     }
     __syncthreads();
-    if (tid < 2 * CT) atomicAdd(reinterpret_cast<unsigned long long*>(a.stats_out) + 2 * (cg * CT) + tid, s_stat[tid]);
+    if (tid < 2 * CT)       // four warp partials -> fixed point -> ONE integer atomic per CTA and slot (order-independent)
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.stats_out) + 2 * (cg * CT) + tid,
+                  stat_fx(s_stat[tid]) + stat_fx(s_stat[2 * CT + tid]) + stat_fx(s_stat[4 * CT + tid]) + stat_fx(s_stat[6 * CT + tid]));
 }
 
 // toplayer: feats = W (32x32) . ABN(conv2.2) + b, one thread per pixel, weights broadcast from shared memory
@@ -275,6 +277,8 @@ int mvsn_featurenet_forward_bn(const float* const* w, float* const* running, int
     int hs[3] = {H, half_up(H), half_up(half_up(H))}, ws[3] = {W, half_up(W), half_up(half_up(W))};
     int rc;
     ActSrc src{imgs, nullptr, nullptr, nullptr, 1.0, nullptr, nullptr};
+    BnUpdateArgs upd{};
+    upd.momentum = momentum;
     int hin = H, win = W;
     for (int l = 0; l < 8; ++l) {
         const int lv = kFLevel[l];
@@ -289,10 +293,13 @@ int mvsn_featurenet_forward_bn(const float* const* w, float* const* running, int
         src.x = a.out; src.stats = a.stats_out; src.gamma = w[3 * l + 1]; src.beta = w[3 * l + 2];
         src.count = (double)V * a.Hout * a.Wout;
         if (bn_mode == MVSN_BN_RUNNING) { src.rmean = running[2 * l]; src.rvar = running[2 * l + 1]; }
-        if (bn_mode == MVSN_BN_BATCH_UPDATE)
-            bn_update_running_kernel<<<1, 64, 0, st>>>(a.stats_out, src.count, a.Cout, momentum, running[2 * l], running[2 * l + 1]);
+        if (bn_mode == MVSN_BN_BATCH_UPDATE) {
+            upd.stats[l] = a.stats_out; upd.count[l] = src.count; upd.C[l] = a.Cout;
+            upd.rmean[l] = running[2 * l]; upd.rvar[l] = running[2 * l + 1];
+        }
         hin = a.Hout; win = a.Wout;
     }
+    if (bn_mode == MVSN_BN_BATCH_UPDATE) bn_update_running_kernel<<<8, 64, 0, st>>>(upd);
     const long long plane = (long long)hin * win;
     toplayer_kernel<<<cdiv((long long)V * plane, 128), 128, 0, st>>>(src, w[24], w[25], V, plane, feats);
     MVSN_CUDA_CHECK(cudaGetLastError());

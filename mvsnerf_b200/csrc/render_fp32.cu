@@ -245,8 +245,14 @@ render_fp32_kernel(const SceneDev sc, const RenderIO io, const float* __restrict
 }
 
 int launch_render_fp32(const SceneDev& sc, const RenderIO& io, bool fast, const float* wts, cudaStream_t stream) {
-    MVSN_CUDA_CHECK(cudaFuncSetAttribute(render_fp32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    MVSN_CUDA_CHECK(cudaFuncSetAttribute(render_fp32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    static bool attr_set[64] = {false};                   // once per device, not per launch
+    int dev = 0;
+    MVSN_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        MVSN_CUDA_CHECK(cudaFuncSetAttribute(render_fp32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        MVSN_CUDA_CHECK(cudaFuncSetAttribute(render_fp32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        if (dev < 64) attr_set[dev] = true;
+    }
     const int R = io.S <= TILE_M ? TILE_M / io.S : 1;
     const int ngroups = (io.N + R - 1) / R;
     const int grid = ngroups < sm_count() ? ngroups : sm_count();

@@ -74,12 +74,13 @@ __device__ __forceinline__ void tmem_wait16(uint32_t (&r)[16]) {
                  :: "memory");
 }
 
-// two fp32 -> packed fp16x2 (low half = first argument), optionally clamped at zero by the converter
+// two fp32 -> packed fp16x2 (low half = first argument), saturating, optionally clamped at zero by the converter
 template <bool RELU>
 __device__ __forceinline__ uint32_t cvt_h2(float lo, float hi) {
     uint32_t r;
-    if (RELU) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
-    else      asm("cvt.rn.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    // .satfinite: a value beyond the fp16 range becomes +-65504 instead of inf (inf x 0-weight = NaN in the next layer)
+    if (RELU) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    else      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
 
@@ -521,8 +522,14 @@ render_tc_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restrict
 
 int launch_render_tc(const SceneDev& sc, const RenderIO& io_in, bool fast, const void* wimg, cudaStream_t stream) {
     RenderIO io = io_in;
-    MVSN_CUDA_CHECK(cudaFuncSetAttribute(render_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    MVSN_CUDA_CHECK(cudaFuncSetAttribute(render_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    static bool attr_set[64] = {false};                   // once per device, not per launch
+    int dev = 0;
+    MVSN_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        MVSN_CUDA_CHECK(cudaFuncSetAttribute(render_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        MVSN_CUDA_CHECK(cudaFuncSetAttribute(render_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+        if (dev < 64) attr_set[dev] = true;
+    }
     // rays per tile: 32 (best gather locality) unless the batch is too small to give every SM a pair of groups
     int rt = 32;
     while (rt > 4 && (io.N + rt - 1) / rt < 2 * sm_count()) rt >>= 1;

@@ -517,8 +517,14 @@ int pack_mlp_tcs(const float* const* w, void* packed, cudaStream_t stream) {
 
 int launch_render_tcs(const SceneDev& sc, const RenderIO& io_in, bool fast, const void* wimg, cudaStream_t stream) {
     RenderIO io = io_in;
-    MVSN_CUDA_CHECK(cudaFuncSetAttribute(render_tcs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    MVSN_CUDA_CHECK(cudaFuncSetAttribute(render_tcs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    static bool attr_set[64] = {false};                   // once per device, not per launch
+    int dev = 0;
+    MVSN_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        MVSN_CUDA_CHECK(cudaFuncSetAttribute(render_tcs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        MVSN_CUDA_CHECK(cudaFuncSetAttribute(render_tcs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        if (dev < 64) attr_set[dev] = true;
+    }
     int rt = 32;                                             // rays per tile, as in the single-fp16 kernel
     while (rt > 4 && (io.N + rt - 1) / rt < sm_count()) rt >>= 1;
     io.rays_per_tile = rt;
