@@ -41,6 +41,7 @@ H, W, PAD, S = 512, 640, 24, 128
 N_RAYS = H * W
 FLOP_PER_RAY = 32_178_176          # 128 x 251 392 MLP FLOPs           
 BYTES_PER_RAY = 51_248             # 128 x 400 B gather + 32 B in + 16 B out
+SPLIT_EXEC = 109_312 / 125_696     # MACs per sample the split kernel executes after folding feature_linear into the views layer
 WEIGHTS = os.path.join(ROOT, "tests", "golden", "mvsnerf_v0_weights.npz")
 METRIC = "rays/sec @ 128 samples, DTU 512x640"
 
@@ -454,10 +455,13 @@ def run_ours(args):
                     "unit": "rays/s", "ms_per_step": ms_s,
                     "e2e": {"value": e2e_s, "unit": "rays/s", "h2d_bytes_per_step": hfr.h2d_bytes * world,
                             "d2h_bytes_per_step": hfr.d2h_bytes * world},
-                    "roofline": {"bound": "tensor", "achieved": tf, "executed": 3 * tf, "peak": pk["bf16_tflops"],
-                                 "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"], "executed_frac": 3 * tf / pk["bf16_tflops"],
+                    "roofline": {"bound": "tensor", "achieved": tf, "executed": 3 * tf * SPLIT_EXEC, "peak": pk["bf16_tflops"],
+                                 "unit": "TFLOP/s", "frac": tf / pk["bf16_tflops"],
+                                 "executed_frac": 3 * tf * SPLIT_EXEC / pk["bf16_tflops"],
                                  "kernel": MODE_KERNEL["split"], "kernel_ms": ks,
-                                 "note": "algorithmic FLOPs; the 2-term split executes 3 MMAs per K-step"},
+                                 "note": "achieved = algorithmic FLOPs of the reference MLP; executed = 3 MMAs per K-step on "
+                                         "the kernel's own network (feature_linear folded into the views layer: 109 312 of "
+                                         "the 125 696 MACs per sample)"},
                     "rgb_linf_vs_fp32_kernel": float((rm - r32).abs().max()), "gate": 1e-4,
                     "note": "MVSN_MLP_TC_SPLIT, the DEFAULT mode of backend.rendering / render_rays"}
 

@@ -25,13 +25,17 @@ namespace mvsn {
 
 using namespace umma;
 
-namespace tcs {     // weight image: the 18 chunks of the single-fp16 mode, each stored as [hi image | lo image]
-constexpr int NCHUNK = 18;
+namespace tcs {     // weight image: 16 chunks in consumption order, each stored as [hi image | lo image]
+// chunks 0..12 as in the single-fp16 round-1 kernel (modulation, layer 0, layers 1..4 x 2 K-blocks, layer 5 x 3);
+// 13, 14: feature_linear and views_linears[0] FOLDED at pack time (no non-linearity between them, models.py:213-218):
+//         W' = Wv[:, :128] Wf (64 rows) + alpha_linear as row 64 (sigma), N = 80; chunk 14 also carries the [dir | 1] tile;
+// 15: rgb_linear.   8 GEMM phases per tile instead of 9.
+constexpr int NCHUNK = 16;
 __host__ __device__ constexpr int part_bytes(int c) {           // bytes of ONE part (hi or lo) of chunk c
     return c == 0 || c == 1 || c == 2 || c == 4 || c == 6 || c == 8 || c == 10 || c == 11 || c == 12 ? 16384
          : c == 3 || c == 5 || c == 7 || c == 9 ? 20480
-         : c == 13 ? 18432 : c == 14 ? 23552 /* 23 040 padded: the lo image must start 1024-aligned */
-         : c == 15 ? 8192 : c == 16 ? 10240 : 2048;
+         : c == 13 ? 10240 : c == 14 ? 13312 /* 10 240 + 2 560 padded: the lo image must start 1024-aligned */
+         : 2048;
 }
 __host__ __device__ constexpr int chunk_offset(int c) {
     int o = 0;
@@ -41,8 +45,9 @@ __host__ __device__ constexpr int chunk_offset(int c) {
 constexpr int STREAM_BYTES = chunk_offset(NCHUNK);
 constexpr int TAIL_OFFSET = STREAM_BYTES;                   // fp32 tail: rgb_linear.bias[3], 0
 constexpr int TOTAL_BYTES = STREAM_BYTES + 16;
-constexpr int STAGE_BYTES = 47104;                          // = 2 x 23 552 (largest chunk), 1024-aligned
+constexpr int STAGE_BYTES = 40960;                          // = 2 x 20 480 (largest chunk), 1024-aligned
 constexpr int NSTAGE = 2;
+constexpr int N_VIEWS_OP = 80;                              // 64 views-layer outputs + sigma + 15 zero rows
 }  // namespace tcs
 
 namespace {
@@ -64,17 +69,17 @@ struct Shared {
     Cams cams;
 };
 
-__constant__ int c_op_nblk[9] = {2, 2, 2, 2, 2, 3, 2, 2, 1};
-__constant__ uint32_t c_op_idesc[9] = {idesc_f16(128, 128), idesc_f16(128, 128), idesc_f16(128, 128), idesc_f16(128, 128),
-                                       idesc_f16(128, 128), idesc_f16(128, 128), idesc_f16(128, 144), idesc_f16(128, 64),
-                                       idesc_f16(128, 16)};
-__constant__ int c_blk_chunk[9][3] = {{0, 1, 0}, {2, 3, 0}, {4, 5, 0}, {6, 7, 0}, {8, 9, 0}, {10, 11, 12}, {13, 14, 0}, {15, 16, 0}, {17, 0, 0}};
-__constant__ uint32_t c_blk_aoff[9][3] = {{OFF_MISC, OFF_PE, 0}, {OFF_H0, OFF_H1, 0}, {OFF_H0, OFF_H1, 0}, {OFF_H0, OFF_H1, 0}, {OFF_H0, OFF_H1, 0},
-                                          {OFF_PE, OFF_H0, OFF_H1}, {OFF_H0, OFF_H1, 0}, {OFF_H0, OFF_H1, 0}, {OFF_H0, 0, 0}};
-// "bias step": A = 16 MISC columns holding a constant one (cols 16..31 for the trunk, 32..47 = [dir, 1] for the views layer),
-// B = a 16-wide no-swizzle tile stored after the K-block inside the op's last chunk (byte offset inside one part)
-__constant__ uint32_t c_op_bias_aoff[9] = {0, OFF_MISC + 32, OFF_MISC + 32, OFF_MISC + 32, OFF_MISC + 32, 0, OFF_MISC + 32, OFF_MISC + 64, 0};
-__constant__ uint32_t c_op_bias_boff[9] = {0, 16384, 16384, 16384, 16384, 0, 18432, 8192, 0};
+__constant__ int c_op_nblk[8] = {2, 2, 2, 2, 2, 3, 2, 1};
+__constant__ uint32_t c_op_idesc[8] = {idesc_f16(128, 128), idesc_f16(128, 128), idesc_f16(128, 128), idesc_f16(128, 128),
+                                       idesc_f16(128, 128), idesc_f16(128, 128), idesc_f16(128, tcs::N_VIEWS_OP), idesc_f16(128, 16)};
+__constant__ int c_blk_chunk[8][3] = {{0, 1, 0}, {2, 3, 0}, {4, 5, 0}, {6, 7, 0}, {8, 9, 0}, {10, 11, 12}, {13, 14, 0}, {15, 0, 0}};
+__constant__ uint32_t c_blk_aoff[8][3] = {{OFF_MISC, OFF_PE, 0}, {OFF_H0, OFF_H1, 0}, {OFF_H0, OFF_H1, 0}, {OFF_H0, OFF_H1, 0}, {OFF_H0, OFF_H1, 0},
+                                          {OFF_PE, OFF_H0, OFF_H1}, {OFF_H0, OFF_H1, 0}, {OFF_H0, 0, 0}};
+// "bias step": A = 16 MISC columns holding a constant one (cols 16..31 for the trunk, 32..47 = [dir, 1] for the folded views
+// layer), B = a 16-wide no-swizzle tile stored after the K-block inside the op's last chunk (byte offset inside one part)
+__constant__ uint32_t c_op_bias_aoff[8] = {0, OFF_MISC + 32, OFF_MISC + 32, OFF_MISC + 32, OFF_MISC + 32, 0, OFF_MISC + 64, 0};
+__constant__ uint32_t c_op_bias_boff[8] = {0, 16384, 16384, 16384, 16384, 0, 10240, 0};
+constexpr int OP_VIEWS = 6;
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
@@ -177,7 +182,7 @@ render_tcs_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restric
         float sigma = 0.f;
         int g_cur = 0, tile_cur = 0;
         bool act_cur = false;
-        // rotated by one tile: the next tile's operand tiles are built between op 7 and op 8 of the tile in flight
+        // rotated by one tile: the next tile's operand tiles are built between op 6 and op 7 (rgb) of the tile in flight
         for (int t = -1; t < ntiles; ++t) {
             if (act_cur) {
                 // ---- trunk ops 0..5: h = relu((W h + b) * modulation)
@@ -190,27 +195,18 @@ render_tcs_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restric
                     fence_proxy_async();
                     mbar_arrive(&sh.in_ready);
                 }
-                // ---- op 6: feature (128 cols) + sigma (col 128)
-                {
-                    mbar_wait(&sh.acc_ready, par_acc); par_acc ^= 1;
-                    tc_fence_after();
-                    epilogue<64, false, false>(t_acc + part * 64, t_mod, hblk, row, 0, 1.f / SW);                              // 16 f
-                    sigma = 0.f;
-                    if (part == 0) {
-                        uint32_t r16[16];
-                        tmem_ld16(t_acc + 128, r16);
-                        tmem_wait16(r16);
-                        sigma = fmaxf(__uint_as_float(r16[0]) * (1.f / (SA * SW)), 0.f);
-                    }
-                    tc_fence_before();
-                    fence_proxy_async();
-                    mbar_arrive(&sh.in_ready);
-                }
-                // ---- op 7: views layer (64 cols), hv -> H0 (hi/lo)
+                // ---- op 6: folded feature -> views layer (64 cols, relu) + sigma (col 64); hv -> H0 (hi/lo)
                 {
                     mbar_wait(&sh.acc_ready, par_acc); par_acc ^= 1;
                     tc_fence_after();
                     epilogue<32, false, true>(t_acc + part * 32, t_mod, smem + OFF_H0, row, part * 4, 1.f / SW);                // 16 hv
+                    sigma = 0.f;
+                    if (part == 0) {
+                        uint32_t r16[16];
+                        tmem_ld16(t_acc + 64, r16);
+                        tmem_wait16(r16);
+                        sigma = fmaxf(__uint_as_float(r16[0]) * (1.f / (SA * SW)), 0.f);
+                    }
                     tc_fence_before();
                     fence_proxy_async();
                     mbar_arrive(&sh.in_ready);
@@ -312,9 +308,9 @@ render_tcs_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restric
             }
             if (act_cur) {
                 if (part == 1) {
-                    mbar_wait(&sh.acc_ready, par_acc); par_acc ^= 1;     // op 8 retired (keeps the barrier phases aligned)
+                    mbar_wait(&sh.acc_ready, par_acc); par_acc ^= 1;     // op 7 retired (keeps the barrier phases aligned)
                 } else {
-                    // ---- op 8: rgb
+                    // ---- op 7: rgb
                     float cr, cg, cb;
                     {
                         mbar_wait(&sh.acc_ready, par_acc); par_acc ^= 1;
@@ -383,7 +379,7 @@ render_tcs_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restric
 #pragma unroll 1
         for (int t = 0; t < ntiles; ++t) {
 #pragma unroll 1
-            for (int op = 0; op < 9; ++op) {
+            for (int op = 0; op < 8; ++op) {
                 const int nblk = c_op_nblk[op];
                 const uint32_t idesc = c_op_idesc[op];
                 mbar_wait(&sh.in_ready, par_in); par_in ^= 1;
@@ -414,7 +410,7 @@ render_tcs_kernel(const SceneDev sc, const RenderIO io, const uint8_t* __restric
                             const uint32_t boff = c_op_bias_boff[op];
                             mma_f16(d, dsw(ab), dns(w_hi + boff), idesc, 1);
                             mma_f16(d, dsw(ab), dns(w_lo + boff), idesc, 1);
-                            if (op == 7) mma_f16(d, dsw(ab + LO), dns(w_hi + boff), idesc, 1);   // dir_lo * W_hi
+                            if (op == OP_VIEWS) mma_f16(d, dsw(ab + LO), dns(w_hi + boff), idesc, 1);   // dir_lo * W_hi
                         }
                         if (last_blk) mma_commit(&sh.acc_ready);
                         mma_commit(&sh.w_empty[st]);                                   // strict full/empty alternation per stage
@@ -487,17 +483,37 @@ __global__ void pack_mlp_tcs_kernel(MlpPtrs w, uint8_t* __restrict__ out) {
         for (int i = tid; i < 128 * 64; i += nt) { const int r = i / 64, k = i % 64;
             put(sw128_offset(r, k), w.p[10][r * 191 + 63 + kb * 64 + k]); }
     } else if (c == 13 || c == 14) {
+        // folded views layer: rows n < 64: W'[n][k] = sum_j Wv[n][j] Wf[j][k] (fp64) ; row 64: alpha_linear ; rows 65..79 zero
         const int kb = c - 13;
-        for (int i = tid; i < 129 * 64; i += nt) { const int r = i / 64, k = i % 64;
-            put(sw128_offset(r, k), r < 128 ? w.p[16][r * 128 + kb * 64 + k] : w.p[18][kb * 64 + k]); }
-        if (kb == 1) for (int r = tid; r < 129; r += nt) put(18432 + nosw_offset(r, 4), r < 128 ? w.p[17][r] : w.p[19][0]);
-    } else if (c == 15 || c == 16) {
-        const int kb = c - 15;
-        for (int i = tid; i < 64 * 64; i += nt) { const int r = i / 64, k = i % 64;
-            put(sw128_offset(r, k), w.p[14][r * 131 + kb * 64 + k]); }
-        if (kb == 1) for (int i = tid; i < 64 * 4; i += nt) { const int r = i / 4, k = i % 4;
-            put(8192 + nosw_offset(r, k), k < 3 ? w.p[14][r * 131 + 128 + k] : w.p[15][r]); }
-    } else if (c == 17) {
+        for (int i = tid; i < 65 * 64; i += nt) {
+            const int r = i / 64, k = i % 64, kk = kb * 64 + k;
+            float v;
+            if (r < 64) {
+                double acc = 0.0;
+                for (int j = 0; j < 128; ++j) acc += (double)w.p[14][r * 131 + j] * (double)w.p[16][j * 128 + kk];
+                v = (float)acc;
+            } else {
+                v = w.p[18][kk];
+            }
+            put(sw128_offset(r, k), v);
+        }
+        if (kb == 1)            // [dir | 1] tile: k < 3: Wv[:, 128 + k] ; k = 3: b' = Wv[:, :128] bf + bv (row 64: alpha bias)
+            for (int i = tid; i < 65 * 4; i += nt) {
+                const int r = i / 4, k = i % 4;
+                float v = 0.f;
+                if (r < 64) {
+                    if (k < 3) v = w.p[14][r * 131 + 128 + k];
+                    else {
+                        double acc = (double)w.p[15][r];
+                        for (int j = 0; j < 128; ++j) acc += (double)w.p[14][r * 131 + j] * (double)w.p[17][j];
+                        v = (float)acc;
+                    }
+                } else if (k == 3) {
+                    v = w.p[19][0];
+                }
+                put(10240 + nosw_offset(r, k), v);
+            }
+    } else if (c == 15) {
         for (int i = tid; i < 3 * 64; i += nt) { const int r = i / 64, k = i % 64; put(sw128_offset(r, k), w.p[20][r * 64 + k]); }
         if (tid < 4) reinterpret_cast<float*>(out + tcs::TAIL_OFFSET)[tid] = tid < 3 ? w.p[21][tid] : 0.f;
     }
