@@ -166,3 +166,50 @@ def test_autograd_plumbing_of_rendering(monkeypatch):
                             imgs=sc.imgs_raw, network_fn=fn)
     out[0].sum().backward()
     assert volume.feat_volume.grad is not None and all(p.grad is None for p in fn.parameters())
+
+
+def test_ray_marcher_and_ndc_mirrors_match_the_oracle():
+    """backend.ray_marcher / backend.get_ndc_coordinate (the host functions the fine-tuning step calls before `rendering`,
+    data/ray_utils.py:152-197, utils.py:112-146) against the oracle's restatement, bit for bit, incl. lindisp and pad."""
+    from oracle import mvsnerf_oracle as orc
+    sc = synthetic.make_scene(64, 96, pad=8, seed=2)
+    rays = synthetic.scene_rays(sc)[::7].contiguous()
+    for lindisp in (False, True):
+        xyz, ro, rd, z = backend.ray_marcher(rays, N_samples=24, lindisp=lindisp, perturb=0)
+        pts, z2 = orc.march_rays(rays, 24, lindisp)
+        assert torch.equal(xyz, pts) and torch.equal(z, z2)
+        assert torch.equal(ro, rays[:, :3]) and torch.equal(rd, rays[:, 3:6])
+        for pad in (0, 8):
+            ndc = backend.get_ndc_coordinate(sc.pose_source["w2cs"][0], sc.pose_source["intrinsics"][0], xyz,
+                                             torch.tensor([sc.W - 1.0, sc.H - 1.0]), near=sc.near_far[0], far=sc.near_far[1],
+                                             pad=pad, lindisp=lindisp)
+            ref = orc.ndc_coords(sc.pose_source["w2cs"][0], sc.pose_source["intrinsics"][0], xyz, sc.H, sc.W, sc.near_far[0],
+                                 sc.near_far[1], float(pad), lindisp)
+            assert torch.equal(ndc, ref)
+    # perturb > 0: stratified samples stay inside their bins and are reproducible under a seed
+    torch.manual_seed(0)
+    _, _, _, za = backend.ray_marcher(rays, N_samples=24, perturb=1.0)
+    torch.manual_seed(0)
+    _, _, _, zb = backend.ray_marcher(rays, N_samples=24, perturb=1.0)
+    _, _, _, z0 = backend.ray_marcher(rays, N_samples=24, perturb=0)
+    assert torch.equal(za, zb) and not torch.equal(za, z0)
+    mid = 0.5 * (z0[:, 1:] + z0[:, :-1])
+    assert bool((za[:, 1:-1] >= mid[:, :-1] - 1e-6).all()) and bool((za[:, 1:-1] <= mid[:, 1:] + 1e-6).all())
+
+
+def test_finetuner_and_backward_refuse_cpu_tensors():
+    fn = backend.MVSNeRF()
+    vol = backend.RefVolume(torch.zeros(1, 8, 8, 8, 8))
+    sc = synthetic.make_scene(32, 32, pad=0, seed=0)
+    with pytest.raises(RuntimeError):
+        backend.FineTuner(fn, vol, sc.imgs_raw, sc.pose_source)
+    with pytest.raises(RuntimeError):
+        backend.render_backward(sc.pose_source, torch.zeros(4, 8, 3), torch.zeros(4, 8, 3), torch.zeros(4, 8), torch.zeros(4, 3),
+                                vol, sc.imgs_raw, fn, grads={"rgb": torch.zeros(4, 3)})
+
+
+def test_pack_pixels_layout():
+    from mvsnerf_b200.distributed import pack_pixels
+    rgb, depth = torch.arange(12.0).view(4, 3), torch.arange(4.0) + 100
+    px = pack_pixels(rgb, depth)
+    assert px.shape == (4, 4) and torch.equal(px[:, :3], rgb) and torch.equal(px[:, 3], depth)

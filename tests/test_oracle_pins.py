@@ -62,3 +62,22 @@ def test_live_reference_eval_mode_vs_oracle(live, weights):
     assert (vol - vol_ref).abs().max() < 2e-4 * max(1.0, float(vol_ref.abs().max()))
     vol_train = orc.encode_volume(sc.imgs_norm, sc.proj_mats, sc.near_far, sc.pad, weights)
     assert (vol - vol_train).abs().max() > 0.1          # the two modes differ grossly with this checkpoint
+
+
+def test_host_mirrors_of_ray_marcher_and_ndc_vs_live_reference(live):
+    """mvsnerf_b200.backend.ray_marcher / get_ndc_coordinate (what the fine-tuning step calls before `rendering`) against
+    the reference's own data/ray_utils.ray_marcher and utils.get_ndc_coordinate, bit for bit."""
+    from mvsnerf_b200 import backend
+    sc = synthetic.make_scene(64, 96, pad=4, seed=13)
+    rays = synthetic.scene_rays(sc)[::9].contiguous()
+    ref = live.ref
+    for lindisp in (False, True):
+        xyz_r, ro_r, rd_r, z_r = ref.ray_utils.ray_marcher(rays, N_samples=20, lindisp=lindisp)
+        xyz, ro, rd, z = backend.ray_marcher(rays, N_samples=20, lindisp=lindisp)
+        assert torch.equal(xyz, xyz_r) and torch.equal(z, z_r) and torch.equal(rd, rd_r)
+        inv = torch.tensor([sc.W - 1, sc.H - 1])
+        a = ref.utils.get_ndc_coordinate(sc.pose_source["w2cs"][0], sc.pose_source["intrinsics"][0].clone(), xyz_r, inv,
+                                         near=sc.near_far[0], far=sc.near_far[1], pad=4.0, lindisp=lindisp)
+        b = backend.get_ndc_coordinate(sc.pose_source["w2cs"][0], sc.pose_source["intrinsics"][0].clone(), xyz, inv,
+                                       near=sc.near_far[0], far=sc.near_far[1], pad=4.0, lindisp=lindisp)
+        assert torch.equal(a, b)
