@@ -395,6 +395,24 @@ def run_ours(args):
             return world * N_RAYS * n_steps / t, hfr
         e2e_value, hfr = e2e_run(mode, args.steps)
 
+        # the same loop fed the way the reference's video notebook feeds it: one camera pose per frame from the host, rays
+        # generated on the device (data/ray_utils.get_rays -> mvsn_make_rays); reported beside `e2e`, not instead of it
+        e2e_cam = None
+        if world == 1:
+            poses = [path[(args.warmup + i) % len(path)].pin_memory() for i in range(args.steps)]
+            for i in range(2):
+                hfr.render_camera(poses[i % len(poses)], d.directions, vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD),
+                                  N_samples=S, mlp_mode=mode)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                hfr.render_camera(poses[i], d.directions, vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(PAD),
+                                  N_samples=S, mlp_mode=mode)
+            torch.cuda.synchronize()
+            e2e_cam = {"value": N_RAYS * args.steps / (time.perf_counter() - t0), "unit": "rays/s", "h2d_bytes_per_step": 64,
+                       "d2h_bytes_per_step": hfr.d2h_bytes,
+                       "api": "HostFrameRenderer.render_camera: pinned c2w -> H2D -> mvsn_make_rays -> mvsn_render_rays -> D2H"}
+
         # ---- strong scaling (BASELINE configs 2 and 4 as ONE job): one frame / one 4096-ray batch sharded over the
         # ranks through the shipped API (distributed.render_rays_sharded), bit-equal to the single-GPU result ----
         strong = {}
@@ -513,6 +531,8 @@ def run_ours(args):
             "strong_scaling": strong,
             "clocks": clocks, "wall_s_timed_region": t_wall,
         }
+        if e2e_cam:
+            line["e2e_camera"] = e2e_cam
         if trace:
             line["step_trace"] = trace
         if alt:

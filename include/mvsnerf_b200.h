@@ -127,6 +127,13 @@ int mvsn_render_rays(const mvsn_render_scene* scene, const mvsn_ray_params* rp,
                      float* rgb, float* depth, float* weights, float* alpha, float* input_feat,
                      void* stream);
 
+/* Ray generation for one camera (replaces: data/ray_utils.get_rays, data/ray_utils.py:32-53, and the notebooks'
+ * `torch.cat([rays_o, rays_d, near, far])`): directions [n,3] = get_ray_directions(H, W, focal) in camera coordinates
+ * (resident on the device, they depend on the intrinsics only), c2w = the first three rows of the camera-to-world matrix,
+ * row-major with row stride 4 ([3,4] or [4,4]), on the device.  rays [n,8] = (c2w[:3,3], directions @ c2w[:3,:3]^T,
+ * near, far): the input of mvsn_render_rays, so a frame needs 48 bytes of host input. */
+int mvsn_make_rays(const float* directions, const float* c2w, float near, float far, int n, float* rays, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Fine-tuning step  (replaces: autograd through renderer.rendering + torch.optim.Adam in
  *   train_mvs_nerf_finetuning_pl.py:140-189 -- gradients of the 22 MLP tensors, models.py:145-222, and of

@@ -895,6 +895,22 @@ def render_rays(rays, volume_feature, imgs, pose_ref, network_fn, near_far, pad,
     return rgb, depth
 
 
+def get_rays(directions, c2w, near, far, out=None):
+    """data/ray_utils.py:32-53 (get_rays) + the notebooks' `cat([rays_o, rays_d, near, far])` in one launch:
+    directions [H,W,3] or [n,3] (camera frame, on the device), c2w [3,4] / [4,4] on the device -> rays [n,8]."""
+    lib = _lib.load()
+    d = _lib.dev_f32(directions.reshape(-1, 3), "directions")
+    m = _lib.dev_f32(c2w, "c2w")
+    if m.dim() != 2 or m.shape[1] != 4 or m.shape[0] < 3 or m.device != d.device:
+        raise RuntimeError(f"get_rays: c2w must be [3,4] or [4,4] on {d.device}, got {tuple(m.shape)} on {m.device}")
+    n = d.shape[0]
+    rays = torch.empty(n, 8, dtype=torch.float32, device=d.device) if out is None else out
+    with torch.cuda.device(d.device):
+        _lib.check(lib.mvsn_make_rays(_lib.ptr(d), _lib.ptr(m), float(near), float(far), n, _lib.ptr(rays), _lib.stream_ptr()),
+                   "mvsn_make_rays")
+    return rays
+
+
 class HostFrameRenderer:
     """Host-buffer entry: rays arrive in (pinned) host memory, pixels are returned in host memory.
 
@@ -917,6 +933,29 @@ class HostFrameRenderer:
         if rays_host.is_cuda or tuple(rays_host.shape) != (self.n, 8):
             raise RuntimeError(f"HostFrameRenderer: expected a host tensor [{self.n}, 8]")
         self.rays_dev.copy_(rays_host, non_blocking=True)
+        render_rays(self.rays_dev, volume_feature, imgs, pose_ref, network_fn, near_far, pad,
+                    out=(self.rgb_dev, self.depth_dev), **kw)
+        if after_launch is not None:
+            after_launch()
+        self.rgb_host.copy_(self.rgb_dev, non_blocking=True)
+        self.depth_host.copy_(self.depth_dev, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self.rgb_host, self.depth_host
+
+    def render_camera(self, c2w_host, directions_dev, volume_feature, imgs, pose_ref, network_fn, near_far, pad,
+                      ray_near_far=None, after_launch=None, **kw):
+        """The notebooks' frame loop as it is actually fed (renderer_video.ipynb: one `c2w` per frame, `get_rays` on the
+        device): the host input of a frame is the camera pose (pinned [4,4] or [3,4] tensor, 48-64 bytes H2D), the rays
+        are generated on the device (mvsn_make_rays) from the resident `directions_dev` [H*W,3], pixels come back to
+        pinned host memory."""
+        if c2w_host.is_cuda or directions_dev.reshape(-1, 3).shape[0] != self.n:
+            raise RuntimeError(f"HostFrameRenderer.render_camera: expected a host c2w and {self.n} device directions")
+        if not hasattr(self, "c2w_dev"):
+            self.c2w_dev = torch.empty(4, 4, dtype=torch.float32, device=self.device)
+        rows = c2w_host.shape[0]
+        self.c2w_dev[:rows].copy_(c2w_host, non_blocking=True)
+        nf = near_far if ray_near_far is None else ray_near_far
+        get_rays(directions_dev, self.c2w_dev, nf[0], nf[1], out=self.rays_dev)
         render_rays(self.rays_dev, volume_feature, imgs, pose_ref, network_fn, near_far, pad,
                     out=(self.rgb_dev, self.depth_dev), **kw)
         if after_launch is not None:

@@ -56,6 +56,23 @@ __global__ void vol_from_cl_kernel(const float4* __restrict__ src, float* __rest
     }
 }
 
+// rays [n][8] = (origin, direction, near, far) of one camera: d = directions @ c2w[:3,:3]^T, o = c2w[:3,3]
+// (data/ray_utils.py:32-53 get_rays + the notebooks' cat with near / far)
+__global__ void make_rays_kernel(const float* __restrict__ dirs, const float* __restrict__ c2w, float near, float far, int n,
+                                 float4* __restrict__ rays) {
+    __shared__ float m[12];
+    if (threadIdx.x < 12) m[threadIdx.x] = __ldg(c2w + threadIdx.x);           // rows of [R | t], row-major [.,4]
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float x = __ldg(dirs + 3 * (size_t)i), y = __ldg(dirs + 3 * (size_t)i + 1), z = __ldg(dirs + 3 * (size_t)i + 2);
+        const float dx = fmaf(z, m[2], fmaf(y, m[1], x * m[0]));
+        const float dy = fmaf(z, m[6], fmaf(y, m[5], x * m[4]));
+        const float dz = fmaf(z, m[10], fmaf(y, m[9], x * m[8]));
+        rays[2 * (size_t)i] = make_float4(m[3], m[7], m[11], dx);
+        rays[2 * (size_t)i + 1] = make_float4(dy, dz, near, far);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // fp32 MLP weight image
 // ------------------------------------------------------------------------------------------
@@ -280,6 +297,17 @@ int mvsn_render_rays_to_peers(const mvsn_render_scene* scene, const mvsn_ray_par
                               float* depth, void* stream) {
     MVSN_REQUIRE(sink != nullptr, MVSN_ENULL, "mvsn_render_rays_to_peers: sink is NULL");
     return render_rays_impl(scene, rp, rays, t_steps, N, S, rgb, depth, nullptr, nullptr, nullptr, sink, stream);
+}
+
+int mvsn_make_rays(const float* directions, const float* c2w, float near, float far, int n, float* rays, void* stream) {
+    MVSN_REQUIRE(directions && c2w && rays, MVSN_ENULL, "mvsn_make_rays: NULL argument");
+    MVSN_REQUIRE(n >= 0, MVSN_EBADSHAPE, "mvsn_make_rays: n=%d", n);
+    MVSN_REQUIRE(aligned16(rays), MVSN_EALIGN, "mvsn_make_rays: rays must be 16-byte aligned");
+    if (n == 0) return MVSN_OK;
+    make_rays_kernel<<<cdiv(n, 256) < 2048 ? cdiv(n, 256) : 2048, 256, 0, (cudaStream_t)stream>>>(
+        directions, c2w, near, far, n, reinterpret_cast<float4*>(rays));
+    MVSN_CUDA_CHECK(cudaGetLastError());
+    return MVSN_OK;
 }
 
 // ---- fine-tuning step ------------------------------------------------------------------------------------

@@ -26,7 +26,7 @@ EXPORTS = [
     "mvsn_featurenet_workspace_bytes", "mvsn_featurenet_forward",
     "mvsn_selftest_umma", "mvsn_debug_set_trace",
     "mvsn_peer_buffer_create", "mvsn_peer_buffer_open", "mvsn_peer_buffer_close", "mvsn_peer_buffer_destroy",
-    "mvsn_render_rays_to_peers",
+    "mvsn_render_rays_to_peers", "mvsn_make_rays",
     "mvsn_featurenet_forward_bn", "mvsn_costreg_forward_bn",
     "mvsn_render_backward_workspace_bytes", "mvsn_render_backward", "mvsn_adam_step", "mvsn_adam_step_volume",
 ]
@@ -104,6 +104,8 @@ def load() -> C.CDLL:
     lib.mvsn_adam_step_volume.argtypes = [vp, vp, vp, vp, C.c_longlong, ip, fp, fp, fp, fp, ip, vp]
     lib.mvsn_costreg_forward_bn.argtypes = [C.POINTER(vp), C.POINTER(vp), ip, fp, vp, ip, ip, ip, vp, vp, C.c_size_t, vp]
     lib.mvsn_featurenet_forward_bn.argtypes = [C.POINTER(vp), C.POINTER(vp), ip, fp, vp, ip, ip, ip, vp, vp, C.c_size_t, vp]
+    lib.mvsn_make_rays.argtypes = [vp, vp, fp, fp, ip, vp, vp]
+    lib.mvsn_make_rays.restype = ip
     lib.mvsn_debug_set_trace.argtypes = [vp]
     lib.mvsn_debug_set_trace.restype = None
     lib.mvsn_selftest_umma.argtypes = [vp, vp, vp, ip, ip, vp, vp]

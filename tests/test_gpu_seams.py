@@ -279,3 +279,29 @@ def test_two_gpu_sharding_nccl_and_peer_stores():
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "multi_gpu_check.py")],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+def test_get_rays_on_device_and_camera_level_host_renderer(scene):
+    """mvsn_make_rays (data/ray_utils.get_rays on the device) against the host construction of the same rays, and
+    HostFrameRenderer.render_camera (host input = the camera pose) against the rays-level call."""
+    sc, d = scene
+    fn, mvs = backend.MVSNeRF().to(DEV), backend.MVSNet().to(DEV).train()
+    backend.load_weights_npz(fn, mvs, WPATH)
+    c2ws = synthetic.spiral_path(sc, 3)
+    with torch.no_grad():
+        vol, _, _ = mvs(d.imgs_norm, d.proj_mats, sc.near_far, pad=sc.pad)
+        hfr = backend.HostFrameRenderer(sc.H * sc.W, DEV)
+        for c2w in c2ws:
+            want = synthetic.camera_rays(sc.directions, c2w, *sc.near_far)                       # host, torch matmul
+            for m in (c2w.to(DEV), c2w[:3].contiguous().to(DEV)):                                # [4,4] and [3,4]
+                got = backend.get_rays(d.directions, m, *sc.near_far)
+                assert got.shape == want.shape
+                assert torch.equal(got[:, :3].cpu(), want[:, :3]) and torch.equal(got[:, 6:].cpu(), want[:, 6:])
+                assert (got[:, 3:6].cpu() - want[:, 3:6]).abs().max().item() <= 2e-7 * want[:, 3:6].abs().max().item()
+            rgb_h, depth_h = hfr.render_camera(c2w.pin_memory(), d.directions, vol, d.imgs_raw, d.pose_source, fn, sc.near_far,
+                                               float(sc.pad), N_samples=32)
+            rgb, depth = backend.render_rays(backend.get_rays(d.directions, c2w.to(DEV), *sc.near_far), vol, d.imgs_raw,
+                                             d.pose_source, fn, sc.near_far, float(sc.pad), N_samples=32)
+            assert torch.equal(rgb_h, rgb.cpu()) and torch.equal(depth_h, depth.cpu())
+            ref_rgb, _ = backend.render_rays(want.to(DEV), vol, d.imgs_raw, d.pose_source, fn, sc.near_far, float(sc.pad), N_samples=32)
+            assert (rgb - ref_rgb).abs().max().item() < 1e-5
