@@ -98,36 +98,15 @@ __device__ __forceinline__ void tma_load_tile(void* smem_dst, const CUtensorMap*
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
 }
-__device__ __forceinline__ void tmem_ld8_c0(uint32_t taddr, uint32_t (&r)[8]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
-}
-// wait for the outstanding tcgen05.ld of this warp; naming the registers keeps their uses below the wait
-__device__ __forceinline__ void tmem_wait24(uint32_t (&a)[16], uint32_t (&b)[8]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
-                 : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]),
-                   "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]),
-                   "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7])
-                 :: "memory");
-}
-__device__ __forceinline__ void tmem_ld4_c0(uint32_t taddr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
-}
 __device__ __forceinline__ void tmem_ld2_c0(uint32_t taddr, uint32_t& r0, uint32_t& r1) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n" : "=r"(r0), "=r"(r1) : "r"(taddr));
 }
+// wait for the outstanding tcgen05.ld of this warp; tying the registers to empty asm statements keeps their uses below it
 __device__ __forceinline__ void tmem_wait54(uint32_t (&r)[54]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 54; i += 6)
         asm volatile("" : "+r"(r[i]), "+r"(r[i + 1]), "+r"(r[i + 2]), "+r"(r[i + 3]), "+r"(r[i + 4]), "+r"(r[i + 5]) :: "memory");
-}
-// same for a 72-column group: the asm cannot name 72 operands, so the registers are tied with an empty asm per 24
-__device__ __forceinline__ void tmem_wait72(uint32_t (&r)[72]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 72; i += 8)
-        asm volatile("" : "+r"(r[i]), "+r"(r[i + 1]), "+r"(r[i + 2]), "+r"(r[i + 3]), "+r"(r[i + 4]), "+r"(r[i + 5]), "+r"(r[i + 6]), "+r"(r[i + 7]) :: "memory");
 }
 __device__ __forceinline__ void split2_c0(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __half2 h = __floats2half2_rn(a, b);
