@@ -670,34 +670,35 @@ __global__ void adam_tensors_kernel(AdamTensors t, AdamScalars a) {
 }
 
 // volume: the gradient is channels-last [nvox][8] (the scatter target) and is ZEROED here for the next step; parameter and
-// moments are channels-last too (PLANAR == false) or planar [8][nvox] (a checkpoint-layout nn.Parameter)
-template <bool PLANAR>
-__global__ void adam_volume_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+// moments here are planar [8][nvox] (a checkpoint-layout nn.Parameter); the channels-last case is adam_volume_cl_kernel
+__global__ void adam_volume_planar_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                    long long nvox, AdamScalars a) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvox; i += (long long)gridDim.x * blockDim.x) {
         float4* g4 = reinterpret_cast<float4*>(g) + 2 * i;
         const float4 ga = g4[0], gb = g4[1];
         g4[0] = make_float4(0.f, 0.f, 0.f, 0.f); g4[1] = make_float4(0.f, 0.f, 0.f, 0.f);
         const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-        if (PLANAR) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const long long j = c * nvox + i;
-                float mm = m[j], vv = v[j];
-                p[j] = adam_update(p[j], gg[c], mm, vv, a);
-                m[j] = mm; v[j] = vv;
-            }
-        } else {
-            float4* p4 = reinterpret_cast<float4*>(p) + 2 * i; float4* m4 = reinterpret_cast<float4*>(m) + 2 * i;
-            float4* v4 = reinterpret_cast<float4*>(v) + 2 * i;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float4 pp = p4[h], mm = m4[h], vv = v4[h];
-                pp.x = adam_update(pp.x, gg[4 * h + 0], mm.x, vv.x, a); pp.y = adam_update(pp.y, gg[4 * h + 1], mm.y, vv.y, a);
-                pp.z = adam_update(pp.z, gg[4 * h + 2], mm.z, vv.z, a); pp.w = adam_update(pp.w, gg[4 * h + 3], mm.w, vv.w, a);
-                p4[h] = pp; m4[h] = mm; v4[h] = vv;
-            }
+        for (int c = 0; c < 8; ++c) {
+            const long long j = c * nvox + i;
+            float mm = m[j], vv = v[j];
+            p[j] = adam_update(p[j], gg[c], mm, vv, a);
+            m[j] = mm; v[j] = vv;
         }
+    }
+}
+
+// channels-last parameter: parameter, moments and gradient share one layout, so the update is purely element-wise --
+// one float4 per thread, consecutive lanes on consecutive 16 bytes (fully coalesced streams)
+__global__ void adam_volume_cl_kernel(float4* __restrict__ p, float4* __restrict__ g, float4* __restrict__ m, float4* __restrict__ v,
+                                      long long n4, AdamScalars a) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 gg = g[i];
+        g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 pp = p[i], mm = m[i], vv = v[i];
+        pp.x = adam_update(pp.x, gg.x, mm.x, vv.x, a); pp.y = adam_update(pp.y, gg.y, mm.y, vv.y, a);
+        pp.z = adam_update(pp.z, gg.z, mm.z, vv.z, a); pp.w = adam_update(pp.w, gg.w, mm.w, vv.w, a);
+        p[i] = pp; m[i] = mm; v[i] = vv;
     }
 }
 
@@ -770,8 +771,9 @@ int launch_adam_volume(float* p, float* g_dhwc, float* m, float* v, long long nv
                        float beta2, float eps, int step, cudaStream_t stream) {
     const AdamScalars a{lr, beta1, beta2, eps, (float)(1.0 - pow((double)beta1, step)), (float)sqrt(1.0 - pow((double)beta2, step))};
     const int grid = sm_count() * 8;
-    if (planar) adam_volume_kernel<true><<<grid, 256, 0, stream>>>(p, g_dhwc, m, v, nvox, a);
-    else        adam_volume_kernel<false><<<grid, 256, 0, stream>>>(p, g_dhwc, m, v, nvox, a);
+    if (planar) adam_volume_planar_kernel<<<grid, 256, 0, stream>>>(p, g_dhwc, m, v, nvox, a);
+    else        adam_volume_cl_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<float4*>(p), reinterpret_cast<float4*>(g_dhwc),
+                                                                reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v), 2 * nvox, a);
     MVSN_CUDA_CHECK(cudaGetLastError());
     return MVSN_OK;
 }
