@@ -19,7 +19,9 @@ supply the *published semantics* of those third-party pieces:
 
   * inplace_abn.InPlaceABN  -- BatchNorm (train: biased batch statistics,
     eval: running statistics), eps 1e-5, momentum 0.1, affine weight used as
-    |gamma|+eps, followed by leaky-ReLU(0.01).  Un-pinned third-party package
+    |gamma|+eps, followed by leaky-ReLU(0.01); a train-mode forward also updates
+    running_mean / running_var (unbiased variance) and counts itself in
+    num_batches_tracked.  Un-pinned third-party package
     (not vendored, not in the reference's install line) => "parity unpinned"
     for this piece; all gamma in ckpts/mvsnerf-v0.tar are > 0.37 so the
     |gamma|+eps vs gamma variant moves RGB by ~3e-5.
@@ -62,6 +64,10 @@ class _InPlaceABN(torch.nn.modules.batchnorm._BatchNorm):
         return
 
     def forward(self, x):
+        # the published ABN counts train-mode forwards like nn.BatchNorm does; the shipped checkpoint's
+        # num_batches_tracked (181165 = its training iterations) is the evidence that the real package did
+        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
+            self.num_batches_tracked.add_(1)
         y = F.batch_norm(x, self.running_mean, self.running_var,
                          self.weight.abs() + self.eps, self.bias,
                          self.training, self.momentum, self.eps)

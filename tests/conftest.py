@@ -54,3 +54,8 @@ def golden_tiny_lindisp():
 @pytest.fixture(scope="session")
 def golden_c1():
     return load_golden("c1_64x64_pad24.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_bn_modes():
+    return load_golden("bn_modes_64x96_pad4.npz")

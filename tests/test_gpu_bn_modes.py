@@ -57,6 +57,41 @@ def test_train_mode_updates_running_statistics_like_batch_norm(weights):
         assert int(sd[key + ".num_batches_tracked"]) == int(weights[name + ".num_batches_tracked"]) + 1
 
 
+def test_both_modes_against_the_reference_fixture(golden_bn_modes):
+    """The same sequence the fixture recorded from the unmodified reference (tests/golden/make_golden_bn.py): a
+    train-mode forward from the shipped state, the running statistics it leaves, then an eval-mode forward."""
+    import collections
+    g = golden_bn_modes
+    Scene = collections.namedtuple("Scene", "imgs proj nf pad")
+    sc = Scene(g["imgs_norm"].to(DEV), g["proj_mats"].to(DEV), g["near_far"].tolist(), int(g["HW_pad"][2]))
+    idx = g["vox_idx"].to(DEV)
+    mvs = backend.MVSNet().to(DEV).train()
+    backend.load_weights_npz(None, mvs, WPATH)
+    with torch.no_grad():
+        vol, _, _ = mvs(sc.imgs, sc.proj, sc.nf, pad=sc.pad)
+    want = g["volume_train_sub"].to(DEV)
+    assert (vol[0].reshape(8, -1)[:, idx] - want).abs().max().item() <= 2e-4 * max(1.0, want.abs().max().item())
+    n = 0
+    for k, v in mvs.state_dict().items():
+        if not k.endswith(("running_mean", "running_var", "num_batches_tracked")):
+            continue
+        ref = g["stats/" + k].to(DEV)
+        if k.endswith("num_batches_tracked"):
+            assert int(v) == int(ref), k
+        else:
+            assert (v - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item()), k
+        n += 1
+    assert n == 54
+    with torch.no_grad():
+        vol_e, feats, _ = mvs.eval()(sc.imgs, sc.proj, sc.nf, pad=sc.pad)
+    want = g["volume_eval_sub"].to(DEV)
+    assert (vol_e[0].reshape(8, -1)[:, idx] - want).abs().max().item() <= 2e-4 * max(1.0, want.abs().max().item())
+    chsum = vol_e[0].double().sum((1, 2, 3)).cpu()
+    assert torch.allclose(chsum, g["volume_eval_chsum"], rtol=1e-4, atol=0.5)
+    fe = g["feats_eval"].to(DEV)
+    assert (feats[0] - fe).abs().max().item() <= 1e-4 * fe.abs().max().item()
+
+
 @pytest.mark.parametrize("D,Hp,Wp", [(16, 24, 40), (24, 16, 64), (16, 40, 72), (32, 48, 56)])
 def test_conv0_tensor_core_kernel_vs_ffma_kernel(D, Hp, Wp):
     """conv0 on tcgen05 (csrc/conv0_tc.cu: TMA-staged tiles, 2-term fp16 split, shifted-tap epilogue) against the

@@ -120,6 +120,36 @@ def test_config1_end_to_end(golden_c1, weights):
     assert (rgb - g["rgb128"]).abs().max() < 2e-5
 
 
+def test_bn_modes_against_reference_fixture(golden_bn_modes, weights):
+    """Both behaviours of the reference's BatchNorm on one scene (tests/golden/make_golden_bn.py): the running statistics
+    a train-mode forward leaves behind (momentum 0.1, unbiased variance; InPlaceABN, models.py:661-685), and the
+    eval-mode forward that then uses them."""
+    g = golden_bn_modes
+    H, W, pad = dims(g)
+    nf = g["near_far"].tolist()
+    idx = g["vox_idx"]
+    rec = {}
+    vol = orc.encode_volume(g["imgs_norm"], g["proj_mats"], nf, pad, weights, record=rec)
+    assert (vol[0].reshape(8, -1)[:, idx] - g["volume_train_sub"]).abs().max() < TOL_VOL
+    assert len(rec) == 18
+    after = dict(weights)
+    for name, (mean, var_unbiased) in rec.items():
+        key = "stats/" + name[len("mvs/"):]
+        want_m, want_v = g[key + ".running_mean"], g[key + ".running_var"]
+        got_m = 0.9 * weights[name + ".running_mean"] + 0.1 * mean
+        got_v = 0.9 * weights[name + ".running_var"] + 0.1 * var_unbiased
+        assert (got_m - want_m).abs().max() <= 1e-5 * max(1.0, float(want_m.abs().max())), name
+        assert (got_v - want_v).abs().max() <= 1e-5 * max(1.0, float(want_v.abs().max())), name
+        assert int(g[key + ".num_batches_tracked"]) == int(weights[name + ".num_batches_tracked"]) + 1
+        after[name + ".running_mean"], after[name + ".running_var"] = want_m, want_v
+    vol_e = orc.encode_volume(g["imgs_norm"], g["proj_mats"], nf, pad, after, eval_mode=True)
+    scale = max(1.0, float(g["volume_eval_sub"].abs().max()))
+    assert (vol_e[0].reshape(8, -1)[:, idx] - g["volume_eval_sub"]).abs().max() < 2e-4 * scale
+    assert torch.allclose(vol_e[0].double().sum((1, 2, 3)), g["volume_eval_chsum"], rtol=1e-4, atol=0.5)
+    f = orc.feature_net(g["imgs_norm"][0], after, eval_mode=True)
+    assert (f - g["feats_eval"]).abs().max() <= 1e-5 * float(g["feats_eval"].abs().max())
+
+
 def test_manual_samplers_match_grid_sample():
     """Pins SURVEY.md App. A1 tap arithmetic (what the CUDA kernels implement) to F.grid_sample."""
     import torch.nn.functional as F
