@@ -59,3 +59,8 @@ def golden_c1():
 @pytest.fixture(scope="session")
 def golden_bn_modes():
     return load_golden("bn_modes_64x96_pad4.npz")
+
+
+@pytest.fixture(scope="session")
+def golden_grad():
+    return load_golden("grad_tiny_32x32_pad4.npz")

@@ -82,6 +82,28 @@ def test_backward_kernel_vs_oracle_autograd_all_outputs(scene, weights, S, n, wh
     _assert_close(g_vol.permute(3, 0, 1, 2).unsqueeze(0).cpu(), vt.grad, 2e-4, "volume")
 
 
+@pytest.mark.parametrize("tag,white", [("s32", False), ("s128w", True)])
+def test_backward_kernel_vs_reference_gradient_fixture(golden_grad, golden_tiny, tag, white):
+    """The fused-loss launch (img2mse formed in the kernel) against gradients the unmodified reference's autograd
+    produced (tests/golden/make_golden_grad.py): loss, every MLP parameter, the encoding volume."""
+    g = {k[len(tag) + 1:]: v for k, v in golden_grad.items() if k.startswith(tag + "/")}
+    t = golden_tiny
+    pose = {"w2cs": t["w2cs"].to(DEV), "c2ws": t["c2ws"].to(DEV), "intrinsics": t["intrinsics"].to(DEV)}
+    fn = backend.MVSNeRF().to(DEV)
+    backend.load_weights_npz(fn, None, WPATH)
+    loss = torch.zeros(1, device=DEV)
+    g_mlp, g_vol, rgb, _ = backend.render_backward(pose, g["xyz"].to(DEV), g["ndc"].to(DEV), g["z"].to(DEV),
+                                                   g["rays"][:, 3:6].to(DEV), t["volume"].to(DEV), t["imgs_raw"].to(DEV), fn,
+                                                   white, target_rgb=g["target"].to(DEV), want_forward=True, loss_out=loss)
+    assert (rgb.cpu() - g["rgb"]).abs().max() < 1e-5
+    assert abs(loss.item() - float(g["loss"])) < 1e-5 * max(1.0, float(g["loss"]))
+    for (name, p), gk in zip(backend._ordered_named_params(fn), g_mlp):
+        _assert_close(gk.cpu(), g["grad_mlp/" + name], 2e-4, name)
+    ref_v = torch.zeros(t["volume"].numel())
+    ref_v[g["grad_volume_idx"]] = g["grad_volume_val"]
+    _assert_close(g_vol.permute(3, 0, 1, 2).reshape(-1).cpu(), ref_v, 2e-4, "volume")
+
+
 def test_autograd_function_kernel_vs_torch_recompute(scene):
     """backend.rendering under autograd: the kernel backward and the PyTorch-recompute backward agree (planar AND
     channels-last RefVolume parameters), and gradients land with the parameter's own layout."""

@@ -1,5 +1,6 @@
 """CPU: the oracle restatement against golden vectors produced by the unmodified reference
 (tests/golden/make_golden.py).  This is what pins oracle/mvsnerf_oracle.py."""
+import pytest
 import torch
 
 from oracle import mvsnerf_oracle as orc
@@ -148,6 +149,32 @@ def test_bn_modes_against_reference_fixture(golden_bn_modes, weights):
     assert torch.allclose(vol_e[0].double().sum((1, 2, 3)), g["volume_eval_chsum"], rtol=1e-4, atol=0.5)
     f = orc.feature_net(g["imgs_norm"][0], after, eval_mode=True)
     assert (f - g["feats_eval"]).abs().max() <= 1e-5 * float(g["feats_eval"].abs().max())
+
+
+@pytest.mark.parametrize("tag,white", [("s32", False), ("s128w", True)])
+def test_finetuning_gradients_against_reference_fixture(golden_grad, golden_tiny, weights, tag, white):
+    """d img2mse / d (MLP parameters, encoding volume) computed by the reference's own autograd through
+    renderer.rendering (tests/golden/make_golden_grad.py) vs autograd through the oracle's restatement."""
+    g = {k[len(tag) + 1:]: v for k, v in golden_grad.items() if k.startswith(tag + "/")}
+    t = golden_tiny
+    wt = {k: v.clone().requires_grad_(k.startswith("mlp/")) for k, v in weights.items()}
+    vol = t["volume"].clone().requires_grad_(True)
+    rgb, _, _, _, _ = orc.render_samples(g["xyz"], g["ndc"], g["z"], g["rays"][:, 3:6], vol, t["imgs_raw"], pose_of(t), wt,
+                                         white_bkgd=white)
+    loss = ((rgb - g["target"]) ** 2).mean()
+    loss.backward()
+    assert (rgb.detach() - g["rgb"]).abs().max() < 2e-6
+    assert abs(loss.item() - float(g["loss"])) < 1e-6
+    n = 0
+    for k, v in g.items():
+        if k.startswith("grad_mlp/"):
+            got = wt["mlp/" + k[len("grad_mlp/"):]].grad
+            assert (got - v).abs().max() <= 2e-5 * float(v.abs().max()) + 1e-9, k
+            n += 1
+    assert n == 22
+    ref_v = torch.zeros(vol.numel())
+    ref_v[g["grad_volume_idx"]] = g["grad_volume_val"]
+    assert (vol.grad.reshape(-1) - ref_v).abs().max() <= 2e-5 * float(ref_v.abs().max())
 
 
 def test_manual_samplers_match_grid_sample():
