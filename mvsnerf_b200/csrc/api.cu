@@ -175,6 +175,7 @@ size_t mvsn_mlp_packed_bytes(int mode) {
 }
 
 int mvsn_mlp_pack(const float* const* w, int mode, void* packed, size_t packed_bytes, void* stream) {
+    MVSN_RANGE("mvsn_mlp_pack");
     MVSN_REQUIRE(w && packed, MVSN_ENULL, "mvsn_mlp_pack: NULL argument");
     const size_t need = mvsn_mlp_packed_bytes(mode);
     MVSN_REQUIRE(need != 0, MVSN_EUNSUPPORTED, "mvsn_mlp_pack: mode %d not available", mode);
@@ -229,6 +230,7 @@ int mvsn_volume_from_channels_last(const float* src, int D, int Hp, int Wp, floa
 int mvsn_render_samples(const mvsn_render_scene* scene, const float* rays_pts, const float* rays_ndc,
                         const float* z_vals, const float* rays_dir, int N, int S, float* rgb, float* depth,
                         float* weights, float* alpha, float* input_feat, void* stream) {
+    MVSN_RANGE("mvsn_render_samples");
     SceneDev sc;
     int rc = make_scene(scene, sc);
     if (rc) return rc;
@@ -248,6 +250,7 @@ int mvsn_render_samples(const mvsn_render_scene* scene, const float* rays_pts, c
 static int render_rays_impl(const mvsn_render_scene* scene, const mvsn_ray_params* rp, const float* rays,
                             const float* t_steps, int N, int S, float* rgb, float* depth, float* weights,
                             float* alpha, float* input_feat, const mvsn_peer_sink* sink, void* stream) {
+    MVSN_RANGE("mvsn_render_rays");
     SceneDev sc;
     int rc = make_scene(scene, sc);
     if (rc) return rc;
@@ -300,6 +303,7 @@ int mvsn_render_rays_to_peers(const mvsn_render_scene* scene, const mvsn_ray_par
 }
 
 int mvsn_make_rays(const float* directions, const float* c2w, float near, float far, int n, float* rays, void* stream) {
+    MVSN_RANGE("mvsn_make_rays");
     MVSN_REQUIRE(directions && c2w && rays, MVSN_ENULL, "mvsn_make_rays: NULL argument");
     MVSN_REQUIRE(n >= 0, MVSN_EBADSHAPE, "mvsn_make_rays: n=%d", n);
     MVSN_REQUIRE(aligned16(rays), MVSN_EALIGN, "mvsn_make_rays: rays must be 16-byte aligned");
@@ -317,6 +321,7 @@ int mvsn_render_backward(const mvsn_render_scene* scene, const float* const* mlp
                          const float* rays_ndc, const float* z_vals, const float* rays_dir, int N, int S,
                          const mvsn_render_grads* g, float* const* grad_mlp, float* grad_volume_dhwc, void* workspace,
                          size_t workspace_bytes, void* stream) {
+    MVSN_RANGE("mvsn_render_backward");
     SceneDev sc;
     int rc = make_scene(scene, sc);
     if (rc) return rc;
@@ -342,6 +347,7 @@ int mvsn_render_backward(const mvsn_render_scene* scene, const float* const* mlp
 int mvsn_adam_step(float* const* params, const float* const* grads, float* const* exp_avg, float* const* exp_avg_sq,
                    const int* numel_host, int count, float lr, float beta1, float beta2, float eps, int step,
                    void* stream) {
+    MVSN_RANGE("mvsn_adam_step");
     MVSN_REQUIRE(params && grads && exp_avg && exp_avg_sq && numel_host, MVSN_ENULL, "mvsn_adam_step: NULL argument");
     MVSN_REQUIRE(step >= 1, MVSN_EBADSHAPE, "mvsn_adam_step: step=%d (counts from 1)", step);
     return launch_adam_tensors(params, grads, exp_avg, exp_avg_sq, numel_host, count, lr, beta1, beta2, eps, step,
@@ -350,6 +356,7 @@ int mvsn_adam_step(float* const* params, const float* const* grads, float* const
 
 int mvsn_adam_step_volume(float* param, float* grad_dhwc, float* exp_avg, float* exp_avg_sq, long long nvox,
                           int planar, float lr, float beta1, float beta2, float eps, int step, void* stream) {
+    MVSN_RANGE("mvsn_adam_step_volume");
     MVSN_REQUIRE(param && grad_dhwc && exp_avg && exp_avg_sq, MVSN_ENULL, "mvsn_adam_step_volume: NULL argument");
     MVSN_REQUIRE(nvox > 0 && step >= 1, MVSN_EBADSHAPE, "mvsn_adam_step_volume: nvox=%lld step=%d", nvox, step);
     MVSN_REQUIRE(aligned16(grad_dhwc) && (planar || (aligned16(param) && aligned16(exp_avg) && aligned16(exp_avg_sq))),

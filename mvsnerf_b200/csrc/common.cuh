@@ -6,6 +6,8 @@
 #include <cstdarg>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>                 // header-only NVTX v3: a no-op function-pointer check unless a tool is attached
+
 #include "../../include/mvsnerf_b200.h"
 
 namespace mvsn {
@@ -30,6 +32,15 @@ void set_error(const char* fmt, ...);
             return (code);                     \
         }                                      \
     } while (0)
+
+// NVTX range over a C-ABI entry point (the reference has no tracing; nsys / ncu --nvtx see these)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define MVSN_RANGE(name) ::mvsn::NvtxRange mvsn_nvtx_range_(name)
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -564,6 +564,7 @@ int mvsn_costreg_forward(const float* const* w, const float* cost, int D, int Hp
 
 int mvsn_costreg_forward_bn(const float* const* w, float* const* running, int bn_mode, float momentum, const float* cost,
                             int D, int Hp, int Wp, float* volume_dhwc, void* workspace, size_t workspace_bytes, void* stream_) {
+    MVSN_RANGE("mvsn_costreg_forward_bn");
     cudaStream_t st = (cudaStream_t)stream_;
     const bool conv0_ffma_flag = (bn_mode & MVSN_CONV0_FFMA) != 0;
     bn_mode &= ~MVSN_CONV0_FFMA;

@@ -180,6 +180,7 @@ size_t mvsn_cost_volume_workspace_bytes(int V, int h, int w) {
 int mvsn_build_cost_volume(const float* imgs, const float* feats, const float* proj, const float* depths,
                            int V, int H, int W, int D, int pad, float* cost, float* in_masks,
                            void* workspace, size_t workspace_bytes, void* stream_) {
+    MVSN_RANGE("mvsn_build_cost_volume");
     cudaStream_t stream = (cudaStream_t)stream_;
     MVSN_REQUIRE(imgs && feats && proj && depths && cost && workspace, MVSN_ENULL, "mvsn_build_cost_volume: NULL argument");
     MVSN_REQUIRE(V == 3, MVSN_EBADSHAPE, "mvsn_build_cost_volume: V=%d (the cost volume is 9+32 channels = 3 views)", V);

@@ -252,6 +252,7 @@ int mvsn_featurenet_forward(const float* const* w, const float* imgs, int V, int
 
 int mvsn_featurenet_forward_bn(const float* const* w, float* const* running, int bn_mode, float momentum, const float* imgs,
                                int V, int H, int W, float* feats, void* workspace, size_t workspace_bytes, void* stream_) {
+    MVSN_RANGE("mvsn_featurenet_forward_bn");
     cudaStream_t st = (cudaStream_t)stream_;
     MVSN_REQUIRE(bn_mode == MVSN_BN_BATCH || bn_mode == MVSN_BN_BATCH_UPDATE || bn_mode == MVSN_BN_RUNNING, MVSN_EBADSHAPE,
                  "mvsn_featurenet_forward_bn: bn_mode %d", bn_mode);
