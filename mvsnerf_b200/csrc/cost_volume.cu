@@ -63,11 +63,11 @@ struct Taps {              // bilinear taps of one source view for one voxel (ze
     float mask;
 };
 
-__device__ __forceinline__ Taps make_taps(const float* __restrict__ P, float xr, float yr, float depth, int h, int w) {
-    // q = R (x, y, 1)^T + T / depth           utils.py:612
-    float q0 = fmaf(P[1], yr, P[0] * xr) + P[2] + __fdiv_rn(P[3], depth);
-    float q1 = fmaf(P[5], yr, P[4] * xr) + P[6] + __fdiv_rn(P[7], depth);
-    float q2 = fmaf(P[9], yr, P[8] * xr) + P[10] + __fdiv_rn(P[11], depth);
+__device__ __forceinline__ Taps make_taps(const float* __restrict__ P, float xr, float yr, int h, int w) {
+    // q = R (x, y, 1)^T + T / depth           utils.py:612 ; P[3], P[7], P[11] already hold T / depth of this plane
+    float q0 = fmaf(P[1], yr, P[0] * xr) + P[2] + P[3];
+    float q1 = fmaf(P[5], yr, P[4] * xr) + P[6] + P[7];
+    float q2 = fmaf(P[9], yr, P[8] * xr) + P[10] + P[11];
     float u = __fdiv_rn(q0, q2), v = __fdiv_rn(q1, q2);                       // :617
     float gx = __fdiv_rn(u, (float)(((double)w - 1.0) / 2.0)) - 1.f;           // :619-620
     float gy = __fdiv_rn(v, (float)(((double)h - 1.0) / 2.0)) - 1.f;
@@ -99,11 +99,17 @@ cost_volume_kernel(const CostArgs a) {
     const int hp = a.h + 2 * a.pad, wp = a.w + 2 * a.pad;
     const long long plane = (long long)hp * wp, nvox = plane * a.D;
     const int hw = a.h * a.w;
-    __shared__ float s_proj[36];
-    if (threadIdx.x < 36) s_proj[threadIdx.x] = __ldg(a.proj + threadIdx.x);
-    __syncthreads();
     // grid = (plane tiles, D): one voxel per thread, the depth index is the block's y coordinate (no 64-bit division)
     const int d = blockIdx.y;
+    // the block's depth plane is fixed, so the translation column is divided by the depth once per block (same IEEE
+    // division, same operands as the per-voxel form: bit-identical) instead of six times per voxel
+    __shared__ float s_proj[36];
+    if (threadIdx.x < 36) {
+        float p = __ldg(a.proj + threadIdx.x);
+        if ((threadIdx.x & 3) == 3) p = __fdiv_rn(p, __ldg(a.depths + d));
+        s_proj[threadIdx.x] = p;
+    }
+    __syncthreads();
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < (int)plane) {
         const long long i = (long long)d * plane + r;
@@ -111,7 +117,6 @@ cost_volume_kernel(const CostArgs a) {
         const int y = yp - a.pad, x = xp - a.pad;
         const bool interior = (unsigned)y < (unsigned)a.h && (unsigned)x < (unsigned)a.w;
         const int ref_off = interior ? y * a.w + x : 0;
-        const float depth = __ldg(a.depths + d);
         float* out = a.cost + i;
 
         Taps t[2];
@@ -119,11 +124,12 @@ cost_volume_kernel(const CostArgs a) {
         if (a.masks) a.masks[i] = 1.f;
 #pragma unroll
         for (int v = 1; v < 3; ++v) {
-            t[v - 1] = make_taps(s_proj + 12 * v, (float)x, (float)y, depth, a.h, a.w);
+            t[v - 1] = make_taps(s_proj + 12 * v, (float)x, (float)y, a.h, a.w);
             nvis += t[v - 1].mask;
             if (a.masks) a.masks[(size_t)v * nvox + i] = t[v - 1].mask;
         }
-        const float inv_n = __fdiv_rn(1.f, nvis);                                 // models.py:889
+        // 1 / (number of visible views), models.py:889: the count is 1, 2 or 3, so the IEEE quotient is one of three constants
+        const float inv_n = nvis == 1.f ? 1.f : (nvis == 2.f ? 0.5f : 0.333333343267440796f);
 
         // the four taps of a 4-channel texel, combined per channel in the reference's tap order (nw, ne, sw, se)
         auto gather4 = [&](const float4* __restrict__ p, const Taps& tp) -> float4 {
