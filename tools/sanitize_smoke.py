@@ -41,14 +41,19 @@ with torch.no_grad():
                 use_color_volume = False
             backend.rendering(A(), d.pose_source, xyz, ndc, z, None, rd, volume_feature=backend.RefVolume(vol.contiguous().clone()),
                               imgs=d.imgs_raw, network_fn=fn, mlp_mode=mode)
+    if not only or "render" in only:
+        dirs = torch.randn(16, 24, 3, device=dev)
+        backend.get_rays(dirs, d.pose_source["c2ws"][0], sc.near_far[0], sc.near_far[1])          # mvsn_make_rays
 if not only or "backward" in only:
-    volume = backend.RefVolume(vol.detach().clone())
-    tuner = backend.FineTuner(fn, volume, d.imgs_raw, d.pose_source, lr=1e-4)
-    for S in (32, 48, 128):
-        xyz, _, rd, z = backend.ray_marcher(rays[:37], N_samples=S, perturb=1.0)
-        ndc = backend.get_ndc_coordinate(d.pose_source["w2cs"][0], d.pose_source["intrinsics"][0], xyz,
-                                         torch.tensor([sc.W - 1.0, sc.H - 1.0], device=dev), near=sc.near_far[0], far=sc.near_far[1],
-                                         pad=sc.pad)
-        tuner.step(xyz, ndc, z, rd, torch.rand(37, 3, device=dev), want_forward=True)
+    # channels-last volume (what MVSNet.forward returns: element-wise Adam kernel), then checkpoint layout (planar kernel)
+    for volume in (backend.RefVolume(vol.detach().clone()), backend.RefVolume(vol.detach().contiguous().clone())):
+        tuner = backend.FineTuner(fn, volume, d.imgs_raw, d.pose_source, lr=1e-4)
+        print("sanitize_smoke: FineTuner planar =", tuner.planar)
+        for S in (32, 48, 128):
+            xyz, _, rd, z = backend.ray_marcher(rays[:37], N_samples=S, perturb=1.0)
+            ndc = backend.get_ndc_coordinate(d.pose_source["w2cs"][0], d.pose_source["intrinsics"][0], xyz,
+                                             torch.tensor([sc.W - 1.0, sc.H - 1.0], device=dev), near=sc.near_far[0],
+                                             far=sc.near_far[1], pad=sc.pad)
+            tuner.step(xyz, ndc, z, rd, torch.rand(37, 3, device=dev), want_forward=True)
 torch.cuda.synchronize()
 print("sanitize_smoke: done")
