@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -56,33 +57,61 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.
+
+    nvidia-smi needs a few hundred ms to come up, longer than a short timed region, so the process is started early
+    (before the scene is built) and streams one line every 25 ms; every line is stamped on arrival and only the lines
+    that arrived inside the marked window [begin(), end()] are used."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc = index, None
+        self.index, self.proc, self.lines, self.thread = index, None, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
+        import threading
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
         except OSError:
             self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.lines.append((time.perf_counter(), line))
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def begin(self):
+        self.t0 = time.perf_counter()
+
+    def end(self):
+        self.t1 = time.perf_counter()
+
+    def in_window(self):
+        t1 = self.t1 if self.t1 is not None else time.perf_counter()
+        return sum(1 for t, _ in list(self.lines) if self.t0 is not None and self.t0 <= t <= t1)
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
-            out, _ = self.proc.communicate(timeout=5)
+            self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-            out, _ = self.proc.communicate()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else float("inf")
         sm, mx, reasons = [], [], set()
-        for line in out.strip().splitlines():
+        for t, line in list(self.lines):
+            if not (t0 <= t <= t1):
+                continue
             f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
@@ -94,7 +123,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "lines_total": len(self.lines)}
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "samples": len(sm), "reasons": sorted(reasons)}
 
@@ -209,6 +238,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     modes = {"fp32": lib.MLP_FP32, "half": lib.MLP_TC_HALF, "split": lib.MLP_TC_SPLIT, "pair": lib.MLP_TC_PAIR}
     mode = modes[args.mode]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                 # early: nvidia-smi is streaming by the time the timed region begins
 
     fn, mvs = backend.MVSNeRF().to(dev), backend.MVSNet().to(dev).train()
     backend.load_weights_npz(fn, mvs, WEIGHTS)
@@ -326,18 +358,26 @@ def run_ours(args):
         return max_over_ranks(tot) / n_steps, kern, rest
 
     with torch.no_grad():
-        sampler = ClockSampler(local)
         for i in range(args.warmup):
             step(i)
         barrier()
-        if rank == 0:
-            sampler.start()
         launches[0] = 0
+        sampler.begin()
         t_wall0 = time.perf_counter()
         ms_per_step, kern_list, rest_list = timed_steps(mode, 0, args.steps)
         t_wall = time.perf_counter() - t_wall0
-        clocks = sampler.stop() if rank == 0 else None
         n_launch = launches[0]
+        # a timed region shorter than a few sampling periods may have caught no clock sample: keep the SAME load running
+        # (untimed, same number of extra steps on every rank) until the window is at least 0.4 s long
+        t_region = ms_per_step * 1e-3 * args.steps                 # max over ranks: identical on every rank
+        if t_region < 0.4:
+            for i in range(int(math.ceil((0.4 - t_region) / (ms_per_step * 1e-3)))):
+                step(i, mode)
+            barrier()
+        sampler.end()
+        clocks = sampler.stop() if rank == 0 else None
+        if clocks is not None and t_region < 0.4:
+            clocks["window"] = "timed region + the same steps continued untimed to 0.4 s"
         value = world * N_RAYS / (ms_per_step * 1e-3)
         kern = sum(kern_list) / len(kern_list)        # the render kernel alone, on the SAME launches as ms_per_step
 
