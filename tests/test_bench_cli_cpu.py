@@ -47,3 +47,30 @@ def test_product_arm_has_no_cpu_fallback():
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout)
     assert not any(l.lstrip().startswith("{") for l in r.stdout.splitlines())
+
+
+def test_clock_sampler_uses_only_lines_that_arrived_inside_the_window(tmp_path, monkeypatch):
+    """The `clocks` object of the bench line: a stand-in nvidia-smi that needs 0.2 s to come up and then streams a line
+    every 25 ms; only lines stamped inside [begin(), end()] count, a window that closes before the first line reports
+    'no samples' (bench.py keeps the load running to 0.4 s so that this cannot happen in a real run)."""
+    import importlib.util
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\nsleep 0.2\nwhile true; do echo '0, 1965, 1980, 700.0, Not Active, Not Active, Not Active, Active'; "
+                    "sleep 0.025; done\n")
+    fake.chmod(0o755)
+    monkeypatch.setenv("PATH", str(tmp_path) + os.pathsep + os.environ["PATH"])
+    monkeypatch.setattr(sys, "argv", ["bench.py"])
+    spec = importlib.util.spec_from_file_location("bench_under_test", BENCH)
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    s.start()
+    time.sleep(0.6)
+    s.begin(); time.sleep(0.2); s.end()
+    out = s.stop()
+    assert out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1980.0 and out["reasons"] == ["sw_power_cap"]
+    assert 2 <= out["samples"] <= 12                               # ~8 lines in 0.2 s, none of the ~16 earlier ones
+    s = bench.ClockSampler(0)
+    s.start(); s.begin(); time.sleep(0.05); s.end()
+    assert s.stop()["reasons"] == ["no samples"]
